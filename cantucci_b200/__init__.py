@@ -1,0 +1,18 @@
+"""cantucci_b200 -- B200-native (sm_100a) implementation of cantucci's hot path.
+
+Mandelbulb distance-estimator sampling over octree-leaf span grids and
+naive-surface-nets mesh extraction, as hand-written CUDA kernels behind a C ABI
+(include/cantucci_b200.h).  This package is the host-side mirror of the
+reference's `Shape` / `MeshBuffer` / `octree::Span` interface over that ABI.
+"""
+from ._lib import (CantucciError, Context, VERTEX_DTYPE, default_context, lib, LIB_PATH)
+from .mesh import MeshBatch, MeshBuffer, Timings, generate_for_boxes, sample_grids
+from .octree import Octree, Span, create_spans, spans_array, startup_tree, tile_volume
+from .shape import Mandelbulb, Shape, Sphere
+
+__all__ = [
+    "CantucciError", "Context", "VERTEX_DTYPE", "default_context", "lib", "LIB_PATH",
+    "MeshBatch", "MeshBuffer", "Timings", "generate_for_boxes", "sample_grids",
+    "Octree", "Span", "create_spans", "spans_array", "startup_tree", "tile_volume",
+    "Mandelbulb", "Shape", "Sphere",
+]

@@ -1,0 +1,178 @@
+"""ctypes binding of libcantucci_b200.so (the C ABI in include/cantucci_b200.h).
+
+There is no CPU fallback: if the CUDA library has not been built, or no CUDA
+device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcantucci_b200.so")
+
+CTC_OK = 0
+CTC_ERR_INVALID_ARGUMENT = 1
+CTC_ERR_CUDA = 2
+CTC_ERR_OVERFLOW = 3
+CTC_ERR_LERP_ASSERT = 4
+CTC_ERR_NO_DEVICE = 5
+
+CTC_SHAPE_MANDELBULB = 0
+CTC_SHAPE_SPHERE = 1
+CTC_MATH_EXACT = 0
+CTC_MATH_FAST = 1
+
+# mesh::Vertex (src/mesh/mod.rs:255-261)
+VERTEX_DTYPE = np.dtype(
+    [("position", "<f4", (3,)), ("normal", "<f4", (3,)), ("distance_from_surface", "<f4")]
+)
+assert VERTEX_DTYPE.itemsize == 28
+
+
+class CtcSpan(C.Structure):
+    _fields_ = [("start", C.c_float * 3), ("end", C.c_float * 3)]
+
+
+class CtcShape(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("power", C.c_uint32),
+        ("max_iters", C.c_uint64),
+        ("bailout", C.c_float),
+        ("center", C.c_float * 3),
+        ("radius", C.c_float),
+        ("flags", C.c_uint32),
+    ]
+
+
+class CtcTimings(C.Structure):
+    _fields_ = [
+        ("first_ms", C.c_double),
+        ("second_ms", C.c_double),
+        ("third_ms", C.c_double),
+        ("vertices", C.c_uint64),
+        ("faces", C.c_uint64),
+    ]
+
+
+# every symbol include/cantucci_b200.h declares
+EXPORTS = (
+    "ctc_version", "ctc_device_count", "ctc_ctx_create", "ctc_ctx_destroy", "ctc_ctx_set_stream",
+    "ctc_ctx_set_group_spans", "ctc_ctx_synchronize", "ctc_last_error", "ctc_kernel_launches",
+    "ctc_de_batch", "ctc_de_batch_device", "ctc_sample_grids", "ctc_sample_grids_device",
+    "ctc_mesh_spans", "ctc_mesh_spans_device", "ctc_mesh_result",
+)
+
+_lib = None
+
+
+class CantucciError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cantucci_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m cantucci_b200.build` "
+            "(there is no CPU fallback)"
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u32, u64p = C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint64)
+    shp, spn = C.POINTER(CtcShape), C.c_void_p
+    L.ctc_version.restype = C.c_int
+    L.ctc_device_count.restype = C.c_int
+    L.ctc_ctx_create.restype = C.c_int
+    L.ctc_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.ctc_ctx_destroy.restype = None
+    L.ctc_ctx_destroy.argtypes = [vp]
+    L.ctc_ctx_set_stream.restype = C.c_int
+    L.ctc_ctx_set_stream.argtypes = [vp, vp]
+    L.ctc_ctx_set_group_spans.restype = C.c_int
+    L.ctc_ctx_set_group_spans.argtypes = [vp, u32]
+    L.ctc_ctx_synchronize.restype = C.c_int
+    L.ctc_ctx_synchronize.argtypes = [vp]
+    L.ctc_last_error.restype = C.c_char_p
+    L.ctc_last_error.argtypes = [vp]
+    L.ctc_kernel_launches.restype = C.c_uint64
+    L.ctc_kernel_launches.argtypes = [vp]
+    for name in ("ctc_de_batch", "ctc_de_batch_device"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, shp, vp, sz, vp]
+    for name in ("ctc_sample_grids", "ctc_sample_grids_device"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, shp, spn, sz, u32, vp]
+    L.ctc_mesh_spans.restype = C.c_int
+    L.ctc_mesh_spans.argtypes = [vp, shp, spn, sz, u32, vp, sz, vp, sz, vp, vp, C.POINTER(CtcTimings)]
+    L.ctc_mesh_spans_device.restype = C.c_int
+    L.ctc_mesh_spans_device.argtypes = [vp, shp, spn, sz, u32, vp, sz, vp, sz, vp, vp]
+    L.ctc_mesh_result.restype = C.c_int
+    L.ctc_mesh_result.argtypes = [vp, u64p, u64p, C.POINTER(CtcTimings)]
+    _lib = L
+    return L
+
+
+class Context:
+    """Owns one ctc_ctx (one CUDA device + stream + workspace)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().ctc_ctx_create(device, C.byref(self._h))
+        if rc != CTC_OK:
+            self._h = C.c_void_p()
+            raise CantucciError(rc, "ctc_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def check(self, rc: int):
+        if rc != CTC_OK:
+            raise CantucciError(rc, lib().ctc_last_error(self._h).decode())
+
+    def last_error(self) -> str:
+        return lib().ctc_last_error(self._h).decode()
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(lib().ctc_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_group_spans(self, n: int):
+        self.check(lib().ctc_ctx_set_group_spans(self._h, n))
+
+    def synchronize(self):
+        self.check(lib().ctc_ctx_synchronize(self._h))
+
+    def kernel_launches(self) -> int:
+        return int(lib().ctc_kernel_launches(self._h))
+
+    def close(self):
+        if self._h:
+            lib().ctc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

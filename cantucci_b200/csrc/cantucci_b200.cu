@@ -1,0 +1,560 @@
+// cantucci_b200.cu -- C ABI over the sm_100a kernels (see include/cantucci_b200.h).
+//
+// Host side of the drop-in boundary: argument checks that mirror the
+// reference's asserts, span geometry, launch grouping, device workspace and the
+// host<->device copies of the host-pointer entry points.  No CPU fallback: if
+// CUDA is unavailable every entry point fails.
+#include "../../include/cantucci_b200.h"
+#include "kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace ctc;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        // grow geometrically to avoid re-allocation churn
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct EventPair { cudaEvent_t a, b; int pass; };
+
+}  // namespace
+
+struct ctc_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t group_spans = 0;   // 0 = auto
+    bool timing = true;
+
+    // workspace
+    DevBuf geom, grids, m_active, m_ex, m_ey, m_ez, m_neg, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
+    DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
+    DevBuf pts_in, pts_out;
+    PinnedBuf h_geom, h_state;
+
+    // events of the last mesh call
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<EventPair> ev_pairs;
+    bool mesh_pending = false;
+};
+
+namespace {
+
+int fail(ctc_ctx* c, int code, const char* what) {
+    if (c) c->err = what;
+    return code;
+}
+int fail_cuda(ctc_ctx* c, cudaError_t e, const char* where) {
+    if (c) { c->err = std::string(where) + ": " + cudaGetErrorString(e); }
+    (void)cudaGetLastError();
+    return CTC_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail_cuda(ctx, _e, #call); } while (0)
+
+// The reference's asserts on the shape (mandelbulb.rs:20) and what this build supports.
+int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
+    if (!s) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "shape is NULL");
+    ShapeDev d{};
+    d.kind = s->kind;
+    if (s->kind == CTC_SHAPE_MANDELBULB) {
+        if (s->max_iters < 1) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "assert!(max_iters >= 1) (mandelbulb.rs:20)");
+        if (s->power < 1 || s->power > 255) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "power must be in 1..=255 (const generic P: u8)");
+        d.power = s->power;
+        d.max_iters = s->max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s->max_iters;
+        d.bailout = s->bailout;
+    } else if (s->kind == CTC_SHAPE_SPHERE) {
+        d.cx = s->center[0]; d.cy = s->center[1]; d.cz = s->center[2]; d.radius = s->radius;
+    } else {
+        return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "unknown shape kind");
+    }
+    if (s->flags & ~(uint32_t)CTC_MATH_FAST) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "unknown shape flags");
+    *out = d;
+    return CTC_OK;
+}
+
+int shape_variant(const ctc_shape* s) {
+    if (s->kind == CTC_SHAPE_SPHERE) return kVarSphere;
+    return s->power == 8 ? kVarP8 : kVarGeneric;
+}
+
+// generate_for_box asserts (buffer.rs:35-39) + GridTable size >= 2 (grid.rs:25)
+int check_spans(ctc_ctx* ctx, const ctc_span* spans, size_t nspans, uint32_t R, uint32_t* lg_out) {
+    if (nspans && !spans) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "spans is NULL");
+    if (R == 0 || (R & (R - 1)) != 0) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "assert!(resolution.is_power_of_two()) (buffer.rs:38-39)");
+    if (R < 2) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "assert!(size >= 2) (grid.rs:25)");
+    if (R > 1024) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "resolution > 1024 needs 64-bit sample indices (unsupported; shard into spans)");
+    if (nspans >= 0xFFFFFFF0ull) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "too many spans");
+    for (size_t i = 0; i < nspans; ++i)
+        for (int c = 0; c < 3; ++c)
+            if (!(spans[i].start[c] < spans[i].end[c]))
+                return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "assert!(span.start < span.end) (buffer.rs:35-37)");
+    uint32_t lg = 0;
+    while ((1u << lg) < R) ++lg;
+    *lg_out = lg;
+    return CTC_OK;
+}
+
+// Span geometry in IEEE f32, no contraction (this TU is built with
+// -ffp-contract=off for the host compiler).  buffer.rs:64-67, 77, 101, 257.
+void make_geom(const ctc_span& sp, uint32_t R, SpanGeom* g) {
+    const float fr = (float)R;
+    for (int c = 0; c < 3; ++c) {
+        volatile float overflow = (sp.end[c] - sp.start[c]) / fr;
+        volatile float s0 = sp.start[c] + (-overflow);
+        volatile float e0 = sp.end[c] + overflow;
+        volatile float across = e0 - s0;
+        volatile float step = across / fr;
+        volatile float t = 0.7f * across;
+        volatile float delta = t / fr;
+        g->s[c] = s0; g->across[c] = across; g->step[c] = step; g->delta[c] = delta;
+    }
+}
+
+struct GroupPlan {
+    uint32_t lg, n, words_per_span, chunk_words, chunks_per_span, group_spans;
+    size_t n3;
+};
+
+GroupPlan plan_groups(const ctc_ctx* ctx, uint32_t R, uint32_t lg, size_t nspans) {
+    GroupPlan p{};
+    p.lg = lg; p.n = R + 1; p.n3 = (size_t)p.n * p.n * p.n;
+    const size_t R3 = (size_t)R * R * R;
+    p.words_per_span = (uint32_t)((R3 + 31) / 32);
+    p.chunk_words = p.words_per_span < kMaxChunkWords ? p.words_per_span : kMaxChunkWords;
+    p.chunks_per_span = p.words_per_span / p.chunk_words;
+    size_t g = ctx->group_spans;
+    if (g == 0) {
+        // keep a group's sample grids around 64 MiB so E1/E3 read them from L2 (126 MB)
+        g = (64ull << 20) / (p.n3 * 4);
+        if (g < 1) g = 1;
+    }
+    const size_t max_by_cells = (size_t)1 << (31 - 3 * lg > 0 ? 31 - 3 * lg : 0);  // span<<lg3 | cell fits u32
+    if (g > max_by_cells) g = max_by_cells;
+    if (g > 32768) g = 32768;                                                      // gridDim.y
+    // chunk-count scan is a single CTA: keep it short
+    const size_t max_by_chunks = (1u << 20) / p.chunks_per_span;
+    if (g > max_by_chunks && max_by_chunks >= 1) g = max_by_chunks;
+    if (g > nspans) g = nspans;
+    if (g < 1) g = 1;
+    p.group_spans = (uint32_t)g;
+    return p;
+}
+
+cudaEvent_t take_event(ctc_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+struct PassTimer {
+    ctc_ctx* ctx; int pass; cudaEvent_t a = nullptr;
+    PassTimer(ctc_ctx* c, int p) : ctx(c), pass(p) {
+        if (ctx->timing) { a = take_event(ctx); if (a) cudaEventRecord(a, ctx->stream); }
+    }
+    ~PassTimer() {
+        if (a) { cudaEvent_t b = take_event(ctx); if (b) { cudaEventRecord(b, ctx->stream); ctx->ev_pairs.push_back({a, b, pass}); } }
+    }
+};
+
+template <bool kFast, int kVariant>
+void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint32_t R, uint32_t lg, float* grids,
+                   size_t stride, uint32_t nspans, size_t n3) {
+    dim3 grid((unsigned)((n3 + kThreads - 1) / kThreads), nspans);
+    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, grids, stride);
+    ctx->launches++;
+}
+
+#define DISPATCH(fast, variant, CALL)                                                       \
+    do {                                                                                    \
+        if (fast) {                                                                         \
+            if ((variant) == kVarP8) { CALL(true, kVarP8); }                                \
+            else if ((variant) == kVarGeneric) { CALL(true, kVarGeneric); }                 \
+            else { CALL(true, kVarSphere); }                                                \
+        } else {                                                                            \
+            if ((variant) == kVarP8) { CALL(false, kVarP8); }                               \
+            else if ((variant) == kVarGeneric) { CALL(false, kVarGeneric); }                \
+            else { CALL(false, kVarSphere); }                                               \
+        }                                                                                   \
+    } while (0)
+
+int upload_geom(ctc_ctx* ctx, const ctc_span* spans, size_t nspans, uint32_t R) {
+    CK(ctx->h_geom.ensure(nspans * sizeof(SpanGeom)));
+    CK(ctx->geom.ensure(nspans * sizeof(SpanGeom)));
+    SpanGeom* hg = static_cast<SpanGeom*>(ctx->h_geom.p);
+    for (size_t i = 0; i < nspans; ++i) make_geom(spans[i], R, &hg[i]);
+    CK(cudaMemcpyAsync(ctx->geom.p, hg, nspans * sizeof(SpanGeom), cudaMemcpyHostToDevice, ctx->stream));
+    return CTC_OK;
+}
+
+int sample_grids_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t R,
+                      float* d_grids) {
+    ShapeDev sh; uint32_t lg;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    rc = check_spans(ctx, spans, nspans, R, &lg); if (rc) return rc;
+    if (nspans == 0) return CTC_OK;
+    if (!d_grids) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "grids is NULL");
+    CK(cudaSetDevice(ctx->device));
+    // the pinned geometry staging buffer may still be in flight from a previous call
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = upload_geom(ctx, spans, nspans, R); if (rc) return rc;
+    const size_t n3 = (size_t)(R + 1) * (R + 1) * (R + 1);
+    const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
+    const int variant = shape_variant(shape);
+    for (size_t s0 = 0; s0 < nspans; s0 += 32768) {
+        const uint32_t cnt = (uint32_t)((nspans - s0) < 32768 ? (nspans - s0) : 32768);
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, ctx->geom.as<SpanGeom>() + s0, R, lg, d_grids + s0 * n3, n3, cnt, n3)
+        DISPATCH(fast, variant, CALL);
+#undef CALL
+    }
+    CK(cudaGetLastError());
+    return CTC_OK;
+}
+
+int de_batch_impl(ctc_ctx* ctx, const ctc_shape* shape, const float* d_xyz, size_t n, float* d_out) {
+    ShapeDev sh;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    if (n == 0) return CTC_OK;
+    if (!d_xyz || !d_out) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL point/output buffer");
+    CK(cudaSetDevice(ctx->device));
+    const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
+    const int variant = shape_variant(shape);
+    const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+#define CALL(F, V) de_batch_kernel<F, V><<<blocks, kThreads, 0, ctx->stream>>>(sh, d_xyz, n, d_out)
+    DISPATCH(fast, variant, CALL);
+#undef CALL
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return CTC_OK;
+}
+
+template <bool kFast, int kVariant>
+void launch_vertex(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, const float* grids, size_t stride, uint32_t R,
+                   uint32_t lg, const uint32_t* cell_of, uint32_t cell_cap, MeshState* st, uint32_t span0, float* out_v,
+                   unsigned long long vcap, unsigned blocks) {
+    vertex_kernel<kFast, kVariant><<<blocks, kThreads, 0, ctx->stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap,
+                                                                         st, span0, out_v, vcap);
+    ctx->launches++;
+}
+
+int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t R,
+                    ctc_vertex* d_v, size_t vcap, uint32_t* d_idx, size_t icap, uint64_t* d_v_off, uint64_t* d_i_off) {
+    ShapeDev sh; uint32_t lg;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    rc = check_spans(ctx, spans, nspans, R, &lg); if (rc) return rc;
+    if (!d_v_off || !d_i_off) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "offset tables are NULL");
+    if ((vcap && !d_v) || (icap && !d_idx)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL output buffer with non-zero capacity");
+    if ((reinterpret_cast<uintptr_t>(d_idx) & 7u) || (reinterpret_cast<uintptr_t>(d_v) & 3u))
+        return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "output buffers must be 8-byte (indices) / 4-byte (vertices) aligned");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));   // staging buffers / events of a previous call
+    ctx->ev_used = 0; ctx->ev_pairs.clear();
+    ctx->mesh_pending = true;
+
+    CK(ctx->state.ensure(sizeof(MeshState)));
+    MeshState* st = ctx->state.as<MeshState>();
+    reset_state_kernel<<<1, 1, 0, ctx->stream>>>(st);
+    ctx->launches++;
+    if (nspans == 0) {
+        CK(cudaMemsetAsync(d_v_off, 0, sizeof(uint64_t), ctx->stream));
+        CK(cudaMemsetAsync(d_i_off, 0, sizeof(uint64_t), ctx->stream));
+        return CTC_OK;
+    }
+    rc = upload_geom(ctx, spans, nspans, R); if (rc) return rc;
+
+    const GroupPlan gp = plan_groups(ctx, R, lg, nspans);
+    const size_t G = gp.group_spans;
+    const size_t words = G * gp.words_per_span, chunks = G * gp.chunks_per_span;
+    const size_t group_cells = G * ((size_t)R * R * R);
+    const uint32_t cell_cap = (uint32_t)(group_cells < vcap ? group_cells : (vcap < 0xFFFFFFFFull ? vcap : 0xFFFFFFFFull));
+    CK(ctx->grids.ensure(G * gp.n3 * sizeof(float)));
+    CK(ctx->m_active.ensure(words * 4)); CK(ctx->m_ex.ensure(words * 4)); CK(ctx->m_ey.ensure(words * 4));
+    CK(ctx->m_ez.ensure(words * 4)); CK(ctx->m_neg.ensure(words * 4));
+    CK(ctx->word_vpre.ensure(words * 4)); CK(ctx->word_qpre.ensure(words * 4));
+    CK(ctx->chunk_counts.ensure(chunks * sizeof(uint2))); CK(ctx->chunk_pre.ensure(chunks * sizeof(uint2)));
+    CK(ctx->cell_of.ensure((size_t)(cell_cap ? cell_cap : 1) * 4));
+    Masks m{ctx->m_active.as<uint32_t>(), ctx->m_ex.as<uint32_t>(), ctx->m_ey.as<uint32_t>(),
+            ctx->m_ez.as<uint32_t>(), ctx->m_neg.as<uint32_t>()};
+
+    const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
+    const int variant = shape_variant(shape);
+    float* grids = ctx->grids.as<float>();
+    const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
+
+    for (size_t s0 = 0; s0 < nspans; s0 += G) {
+        const uint32_t cnt = (uint32_t)((nspans - s0) < G ? (nspans - s0) : G);
+        const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
+        {   // pass 1
+            PassTimer t(ctx, 0);
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3)
+            DISPATCH(fast, variant, CALL);
+#undef CALL
+        }
+        dim3 cgrid(gp.chunks_per_span, cnt);
+        {   // pass 2: classify, scan, vertices
+            PassTimer t(ctx, 1);
+            classify_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(grids, gp.n3, R, lg, gp.words_per_span, gp.chunk_words, m,
+                                                                ctx->chunk_counts.as<uint2>());
+            scan_chunks_kernel<<<1, kScanThreads, 0, ctx->stream>>>(
+                ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
+                (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
+                reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st);
+            apply_prefix_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->chunk_pre.as<uint2>(), gp.words_per_span,
+                                                                    gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
+                                                                    ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
+                                                                    cell_cap);
+            ctx->launches += 3;
+#define CALL(F, V) launch_vertex<F, V>(ctx, sh, geom, grids, gp.n3, R, lg, ctx->cell_of.as<uint32_t>(), cell_cap, st, \
+                                       (uint32_t)s0, reinterpret_cast<float*>(d_v), (unsigned long long)vcap, vblocks)
+            DISPATCH(fast, variant, CALL);
+#undef CALL
+        }
+        {   // pass 3
+            PassTimer t(ctx, 2);
+            quad_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(), R,
+                                                            lg, gp.words_per_span, gp.chunk_words, st, d_idx,
+                                                            (unsigned long long)icap);
+            ctx->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    return CTC_OK;
+}
+
+int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc_timings* timings) {
+    if (!ctx->mesh_pending) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "no mesh call pending");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->h_state.ensure(sizeof(MeshState)));
+    CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const MeshState* st = static_cast<const MeshState*>(ctx->h_state.p);
+    if (n_vertices) *n_vertices = st->total_v;
+    if (n_indices) *n_indices = 6ull * st->total_q;
+    if (timings) {
+        double ms[3] = {0, 0, 0};
+        for (const EventPair& p : ctx->ev_pairs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) ms[p.pass] += t;
+        }
+        timings->first_ms = ms[0]; timings->second_ms = ms[1]; timings->third_ms = ms[2];
+        timings->vertices = st->total_v; timings->faces = st->total_q;
+    }
+    if (st->panic_span != 0xFFFFFFFFu) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "lerp factor outside [0,1] in span %u: the reference panics at math.rs:19", st->panic_span);
+        return fail(ctx, CTC_ERR_LERP_ASSERT, buf);
+    }
+    if (st->overflow) return fail(ctx, CTC_ERR_OVERFLOW, "output capacity too small; required totals reported");
+    return CTC_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int ctc_version(void) { return CTC_VERSION; }
+
+int ctc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ctc_ctx_create(int device, ctc_ctx** out) {
+    if (!out) return CTC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { (void)cudaGetLastError(); return CTC_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return CTC_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return CTC_ERR_CUDA; }
+    ctc_ctx* c = new ctc_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        (void)cudaGetLastError(); delete c; return CTC_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return CTC_OK;
+}
+
+void ctc_ctx_destroy(ctc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->m_ex, &c->m_ey, &c->m_ez, &c->m_neg, &c->chunk_counts,
+                      &c->chunk_pre, &c->word_vpre, &c->word_qpre, &c->cell_of, &c->state, &c->out_v, &c->out_idx,
+                      &c->off_v, &c->off_i, &c->pts_in, &c->pts_out})
+        b->release();
+    c->h_geom.release(); c->h_state.release();
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int ctc_ctx_set_stream(ctc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return CTC_OK;
+}
+
+int ctc_ctx_set_group_spans(ctc_ctx* ctx, uint32_t spans_per_group) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->group_spans = spans_per_group;
+    return CTC_OK;
+}
+
+int ctc_ctx_synchronize(ctc_ctx* ctx) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CTC_OK;
+}
+
+const char* ctc_last_error(const ctc_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+uint64_t ctc_kernel_launches(const ctc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ctc_de_batch_device(ctc_ctx* ctx, const ctc_shape* shape, const float* d_xyz, size_t n, float* d_out) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return de_batch_impl(ctx, shape, d_xyz, n, d_out);
+}
+
+int ctc_de_batch(ctc_ctx* ctx, const ctc_shape* shape, const float* xyz, size_t n, float* out) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    if (n == 0) return CTC_OK;
+    if (!xyz || !out) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL point/output buffer");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->pts_in.ensure(n * 12)); CK(ctx->pts_out.ensure(n * 4));
+    CK(cudaMemcpyAsync(ctx->pts_in.p, xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    rc = de_batch_impl(ctx, shape, ctx->pts_in.as<float>(), n, ctx->pts_out.as<float>()); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->pts_out.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CTC_OK;
+}
+
+int ctc_sample_grids_device(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans,
+                            uint32_t resolution, float* d_grids) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return sample_grids_impl(ctx, shape, spans, nspans, resolution, d_grids);
+}
+
+int ctc_sample_grids(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                     float* grids) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh; uint32_t lg;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    rc = check_spans(ctx, spans, nspans, resolution, &lg); if (rc) return rc;
+    if (nspans == 0) return CTC_OK;
+    if (!grids) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "grids is NULL");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n3 = (size_t)(resolution + 1) * (resolution + 1) * (resolution + 1);
+    // stage through the context's grid buffer in slices of <= 1 GiB
+    size_t per = (1ull << 30) / (n3 * 4);
+    if (per < 1) per = 1;
+    if (per > nspans) per = nspans;
+    CK(ctx->grids.ensure(per * n3 * 4));
+    for (size_t s0 = 0; s0 < nspans; s0 += per) {
+        const size_t cnt = (nspans - s0) < per ? (nspans - s0) : per;
+        rc = sample_grids_impl(ctx, shape, spans + s0, cnt, resolution, ctx->grids.as<float>()); if (rc) return rc;
+        CK(cudaMemcpyAsync(grids + s0 * n3, ctx->grids.p, cnt * n3 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return CTC_OK;
+}
+
+int ctc_mesh_spans_device(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                          ctc_vertex* d_v, size_t vcap, uint32_t* d_idx, size_t icap, uint64_t* d_v_off,
+                          uint64_t* d_i_off) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return mesh_spans_impl(ctx, shape, spans, nspans, resolution, d_v, vcap, d_idx, icap, d_v_off, d_i_off);
+}
+
+int ctc_mesh_result(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc_timings* timings) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return mesh_result_impl(ctx, n_vertices, n_indices, timings);
+}
+
+int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                   ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
+                   ctc_timings* timings) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!v_off || !i_off) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "offset tables are NULL");
+    if ((vcap && !v) || (icap && !idx)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL output buffer with non-zero capacity");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->out_v.ensure((vcap ? vcap : 1) * sizeof(ctc_vertex)));
+    CK(ctx->out_idx.ensure((icap ? icap : 1) * sizeof(uint32_t)));
+    CK(ctx->off_v.ensure((nspans + 1) * 8)); CK(ctx->off_i.ensure((nspans + 1) * 8));
+    int rc = mesh_spans_impl(ctx, shape, spans, nspans, resolution, ctx->out_v.as<ctc_vertex>(), vcap,
+                             ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>());
+    if (rc) return rc;
+    uint64_t nv = 0, ni = 0;
+    const int status = mesh_result_impl(ctx, &nv, &ni, timings);
+    if (status == CTC_ERR_CUDA) return status;
+    CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t cv = nv < vcap ? (size_t)nv : vcap, ci = ni < icap ? (size_t)ni : icap;
+    if (cv) CK(cudaMemcpyAsync(v, ctx->out_v.p, cv * sizeof(ctc_vertex), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ci) CK(cudaMemcpyAsync(idx, ctx->out_idx.p, ci * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// de_device.cuh -- device-side distance estimators (sm_100a).
+//
+// Implements the reference's Shape::min_distance_from for Mandelbulb<P>
+// (/root/reference/src/shape/mandelbulb.rs:59-79, rotate :96-200) and Sphere
+// (src/shape/sphere.rs:33-35) under two arithmetic policies:
+//
+//   MathExact -- every f32 op is a correctly-rounded IEEE op issued through
+//                __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn (never contracted to
+//                FMA, like rustc), in the reference's evaluation order, and
+//                ln() is glibc's logf algorithm.  Power-8 distances are
+//                bit-identical to the reference's x86-64 CPU path.
+//   MathFast  -- FMA-contracted, re-associated polynomial, MUFU rsqrt/rcp/lg2,
+//                squared-radius bailout test, trig-free complex powers for the
+//                generic-P path.  Tolerance mode.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ctc {
+
+struct ShapeDev {
+    int32_t  kind;       // CTC_SHAPE_*
+    uint32_t power;
+    uint32_t max_iters;  // clamped to 2^32-1 on the host
+    float    bailout;
+    float    cx, cy, cz, radius;
+};
+
+// x86's default NaN (sign bit set): what every NaN the reference's DE can
+// produce looks like, so f32::is_sign_positive() classifies it "inside".
+// CUDA's canonical NaN is 0x7FFFFFFF and would classify "outside".
+__device__ __forceinline__ float canonical_x86_nan(float v) {
+    return (v != v) ? __int_as_float(0xFFC00000) : v;
+}
+
+// ---------------------------------------------------------------------------
+// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c, FMA build __logf_fma):
+// 16-entry table + degree-3 polynomial in double.  Third-party algorithm, not
+// part of /root/reference; Rust's f32::ln resolves to it on x86-64 Linux.
+// ---------------------------------------------------------------------------
+__device__ const double kLogfTab[32] = {
+    0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2,
+    0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2, 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3,
+    0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4,
+    0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5, 0x1.0000000000000p+0,  0x0.0p+0,
+    0x1.e608cfd9a47acp-1,  0x1.aa5aa5df25984p-5, 0x1.ca4b31f026aa0p-1,  0x1.c5e53aa362eb4p-4,
+    0x1.b2036576afce6p-1,  0x1.526e57720db08p-3, 0x1.9c2d163a1aa2dp-1,  0x1.bc2860d224770p-3,
+    0x1.886e6037841edp-1,  0x1.1058bc8a07ee1p-2, 0x1.767dcf5534862p-1,  0x1.4043057b6ee09p-2,
+};
+
+__device__ __forceinline__ float logf_glibc(float x) {
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2u == 0u) return __int_as_float(0xff800000);         // log(+-0) = -inf
+        if (ix == 0x7f800000u) return x;                              // log(inf) = inf
+        if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u)             // negative or NaN
+            return __int_as_float(0xFFC00000);
+        ix = __float_as_uint(__fmul_rn(x, 0x1p23f));                  // subnormal: normalise
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double invc = kLogfTab[2 * i], logc = kLogfTab[2 * i + 1];
+    const double z = (double)__uint_as_float(iz);
+    const double r  = __fma_rn(z, invc, -1.0);
+    const double y0 = __fma_rn((double)k, 0x1.62e42fefa39efp-1, logc);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    y = __fma_rn(y, r2, __dadd_rn(y0, r));
+    return __double2float_rn(y);
+}
+
+// ---------------------------------------------------------------------------
+// arithmetic policies
+// ---------------------------------------------------------------------------
+struct MathExact {
+    static constexpr bool kExact = true;
+    __device__ static __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    __device__ static __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    __device__ static __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    __device__ static __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    __device__ static __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    __device__ static __forceinline__ float log(float a) { return logf_glibc(a); }
+};
+
+// f32::powi(n) with constant n, as LLVM expands it (binary square-and-multiply;
+// SURVEY 8a, a7).  n is warp-uniform.
+template <class M>
+__device__ __forceinline__ float powi(float x, uint32_t n) {
+    if (n == 0) return 1.0f;
+    float res = 0.0f, cur = x;
+    bool have = false;
+    while (n) {
+        if (n & 1u) { res = have ? M::mul(res, cur) : cur; have = true; }
+        n >>= 1;
+        if (n) cur = M::mul(cur, cur);
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------------------
+// EXACT: literal evaluation order of the reference
+// ---------------------------------------------------------------------------
+
+// rotate_inner_p8_scalar (mandelbulb.rs:148-200)
+__device__ __forceinline__ void rotate_p8_exact(float x, float y, float z, float& ox, float& oy, float& oz) {
+    using M = MathExact;
+    const float x2 = M::mul(x, x), x4 = M::mul(x2, x2), x6 = M::mul(x4, x2), x8 = M::mul(x4, x4);
+    const float y2 = M::mul(y, y), y4 = M::mul(y2, y2), y6 = M::mul(y4, y2), y8 = M::mul(y4, y4);
+    const float z2 = M::mul(z, z), z4 = M::mul(z2, z2), z6 = M::mul(z4, z2), z8 = M::mul(z4, z4);
+    const float w2 = M::add(x2, y2), w4 = M::mul(w2, w2), w6 = M::mul(w2, w4), w8 = M::mul(w4, w4);
+
+    float t = M::sub(z8, M::mul(M::mul(28.0f, z6), w2));
+    t = M::add(t, M::mul(M::mul(70.0f, z4), w4));
+    t = M::sub(t, M::mul(M::mul(28.0f, z2), w6));
+    const float a = M::add(1.0f, M::div(t, w8));
+
+    float px = M::sub(x8, M::mul(M::mul(28.0f, x6), y2));
+    px = M::add(px, M::mul(M::mul(70.0f, x4), y4));
+    px = M::sub(px, M::mul(M::mul(28.0f, x2), y6));
+    px = M::sub(px, y8);
+    ox = M::mul(a, px);
+
+    float py = M::sub(x6, M::mul(M::mul(7.0f, x4), y2));
+    py = M::add(py, M::mul(M::mul(7.0f, x2), y4));
+    py = M::sub(py, y6);
+    oy = M::mul(M::mul(M::mul(M::mul(8.0f, a), x), y), py);
+
+    const float pz = M::add(M::sub(z4, M::mul(M::mul(6.0f, z2), w2)), w4);
+    oz = M::mul(M::mul(M::mul(M::mul(8.0f, z), M::sqrt(w2)), M::sub(z2, w2)), pz);
+}
+
+// rotate_inner_px_generic::<P> (mandelbulb.rs:128-146).  CUDA's accurate
+// acosf/atan2f/sinf/cosf stand in for glibc's (<= 2 ulp apart): tolerance path.
+__device__ __noinline__ void rotate_generic_exact(uint32_t P, float x, float y, float z, float r,
+                                                  float& ox, float& oy, float& oz) {
+    using M = MathExact;
+    float theta = acosf(M::div(z, r));
+    float phi = atan2f(y, x);
+    const float new_radius = powi<M>(r, P);
+    theta = M::mul(theta, (float)P);
+    phi = M::mul(phi, (float)P);
+    float st, ct, sp, cp;
+    sincosf(theta, &st, &ct);
+    sincosf(phi, &sp, &cp);
+    ox = M::mul(M::mul(st, cp), new_radius);
+    oy = M::mul(M::mul(sp, st), new_radius);
+    oz = M::mul(ct, new_radius);
+}
+
+// rotate_on_z_axis::<P> (mandelbulb.rs:114-126), #[cold]
+__device__ __noinline__ float rotate_on_z_axis_exact(uint32_t P, float z, float r) {
+    using M = MathExact;
+    float theta = acosf(M::div(z, r));      // 0/0 at the origin -> NaN, as in the reference
+    const float new_radius = powi<M>(r, P);
+    theta = M::mul(theta, (float)P);
+    return M::mul(new_radius, cosf(theta));
+}
+
+// Mandelbulb::<P>::min_distance_from (mandelbulb.rs:59-79)
+template <bool kP8>
+__device__ __forceinline__ float mandelbulb_de_exact(const ShapeDev& s, float px, float py, float pz,
+                                                     uint32_t* iters_out = nullptr) {
+    using M = MathExact;
+    const uint32_t P = kP8 ? 8u : s.power;
+    const float fP = (float)P;
+    float zx = px, zy = py, zz = pz;
+    float dr = 1.0f, r = 0.0f;
+    uint32_t it = 0;
+    for (; it < s.max_iters; ++it) {
+        // Vec3::magnitude (mandelbulb.rs:411-418): sqrt((x*x + y*y) + z*z)
+        r = M::sqrt(M::add(M::add(M::mul(zx, zx), M::mul(zy, zy)), M::mul(zz, zz)));
+        if (r > s.bailout) break;
+        // dr = r.powi(P-1) * P * dr + 1.0
+        dr = M::add(M::mul(M::mul(powi<M>(r, P - 1u), fP), dr), 1.0f);
+        float nx, ny, nz;
+        if (zx == 0.0f && zy == 0.0f) {            // is_on_z_axis: x, y are +-0.0
+            nx = 0.0f; ny = 0.0f;
+            nz = rotate_on_z_axis_exact(P, zz, r);
+        } else if (kP8) {
+            rotate_p8_exact(zx, zy, zz, nx, ny, nz);
+        } else {
+            rotate_generic_exact(P, zx, zy, zz, r, nx, ny, nz);
+        }
+        zx = M::add(nx, px); zy = M::add(ny, py); zz = M::add(nz, pz);
+    }
+    if (iters_out) *iters_out = it;
+    const float ln_r = M::mul(M::log(r), r);
+    return canonical_x86_nan(M::div(M::mul(0.5f, ln_r), dr));
+}
+
+// ---------------------------------------------------------------------------
+// FAST: same recurrence, FMA-contracted and re-associated
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float fast_rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float fast_sqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float fast_lg2(float a) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+
+// (a + i b)^n by binary exponentiation, n >= 1 warp-uniform
+__device__ __forceinline__ void cpow(float a, float b, uint32_t n, float& re, float& im) {
+    float cr = a, ci = b;       // running square
+    float rr = 1.0f, ri = 0.0f; // result
+    bool have = false;
+    while (n) {
+        if (n & 1u) {
+            if (have) { const float t = rr * cr - ri * ci; ri = rr * ci + ri * cr; rr = t; }
+            else { rr = cr; ri = ci; have = true; }
+        }
+        n >>= 1;
+        if (n) { const float t = cr * cr - ci * ci; ci = 2.0f * cr * ci; cr = t; }
+    }
+    re = rr; im = ri;
+}
+
+template <bool kP8>
+__device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px, float py, float pz,
+                                                    uint32_t* iters_out = nullptr) {
+    const uint32_t P = kP8 ? 8u : s.power;
+    const float bail2 = s.bailout * s.bailout;
+    float zx = px, zy = py, zz = pz;
+    float dr = 1.0f, r2 = 0.0f;
+    uint32_t it = 0;
+    for (; it < s.max_iters; ++it) {
+        const float x2 = zx * zx, y2 = zy * zy, z2 = zz * zz;
+        const float w2 = x2 + y2;
+        r2 = w2 + z2;
+        if (r2 > bail2) break;                   // r > bailout, on squares
+        const float r = fast_sqrt(r2);
+        float nx, ny, nz;
+        if (kP8) {
+            const float r6 = r2 * r2 * r2;
+            dr = fmaf(8.0f * (r6 * r), dr, 1.0f);
+            if (w2 == 0.0f) {
+                // on the z axis: theta is 0 or pi, cos(8 theta) = 1; origin -> NaN like the reference
+                nx = 0.0f; ny = 0.0f;
+                nz = (r2 == 0.0f) ? __int_as_float(0x7fc00000) : r2 * r6;
+            } else {
+                const float x4 = x2 * x2, y4 = y2 * y2, z4 = z2 * z2, w4 = w2 * w2;
+                const float w6 = w4 * w2, w8 = w4 * w4;
+                // a = 1 + (z8 - 28 z6 w2 + 70 z4 w4 - 28 z2 w6) / w8
+                float t = fmaf(-28.0f * (z4 * z2), w2, z4 * z4);
+                t = fmaf(70.0f * z4, w4, t);
+                t = fmaf(-28.0f * z2, w6, t);
+                const float a = fmaf(t, fast_rcp(w8), 1.0f);
+                // X = a (x8 - 28 x6 y2 + 70 x4 y4 - 28 x2 y6 - y8)   [sic: -y8, as the reference]
+                float qx = fmaf(-28.0f * (x4 * x2), y2, fmaf(x4, x4, -(y4 * y4)));
+                qx = fmaf(70.0f * x4, y4, qx);
+                qx = fmaf(-28.0f * x2, y4 * y2, qx);
+                // Y = 8 a x y (x6 - 7 x4 y2 + 7 x2 y4 - y6)
+                float qy = fmaf(x4, x2, -(y4 * y2));
+                qy = fmaf(-7.0f * x4, y2, qy);
+                qy = fmaf(7.0f * x2, y4, qy);
+                // Z = 8 z sqrt(w2) (z2 - w2)(z4 - 6 z2 w2 + w4)
+                const float qz = fmaf(-6.0f * z2, w2, z4 + w4);
+                nx = a * qx;
+                ny = (8.0f * a) * (zx * zy) * qy;
+                nz = (8.0f * zz) * fast_sqrt(w2) * ((z2 - w2) * qz);
+            }
+        } else {
+            // generic P without trig: (z + i w)^P = r^P (cos P.theta + i sin P.theta),
+            // (x + i y)^P = w^P (cos P.phi + i sin P.phi)
+            float rp1 = 1.0f;                       // r^(P-1)
+            { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
+            dr = fmaf((float)P * rp1, dr, 1.0f);
+            const float w = fast_sqrt(w2);
+            float ct, st;                           // r^P cos(P theta), r^P sin(P theta)
+            cpow(zz, w, P, ct, st);
+            if (w2 == 0.0f) {
+                nx = 0.0f; ny = 0.0f;
+                nz = (r2 == 0.0f) ? __int_as_float(0x7fc00000) : ct;
+            } else {
+                float cp, sp;                       // w^P cos(P phi), w^P sin(P phi)
+                cpow(zx, zy, P, cp, sp);
+                float wp = 1.0f;                    // w^P
+                { float cur = w; uint32_t n = P; while (n) { if (n & 1u) wp *= cur; n >>= 1; if (n) cur *= cur; } }
+                const float sw = st * fast_rcp(wp);
+                nx = sw * cp; ny = sw * sp; nz = ct;
+            }
+        }
+        zx = nx + px; zy = ny + py; zz = nz + pz;
+    }
+    if (iters_out) *iters_out = it;
+    // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
+    const float r = fast_sqrt(r2);
+    const float out = (0.25f * 0.69314718056f) * fast_lg2(r2) * r * fast_rcp(dr);
+    return canonical_x86_nan(out);
+}
+
+// Sphere::min_distance_from (sphere.rs:33-35); cgmath magnitude = sqrt((x*x+y*y)+z*z)
+__device__ __forceinline__ float sphere_de(const ShapeDev& s, float px, float py, float pz) {
+    using M = MathExact;
+    const float dx = M::sub(s.cx, px), dy = M::sub(s.cy, py), dz = M::sub(s.cz, pz);
+    return M::sub(M::sqrt(M::add(M::add(M::mul(dx, dx), M::mul(dy, dy)), M::mul(dz, dz))), s.radius);
+}
+
+// Shape dispatch.  kVariant: 0 = Mandelbulb P=8, 1 = Mandelbulb generic P, 2 = Sphere.
+enum : int { kVarP8 = 0, kVarGeneric = 1, kVarSphere = 2 };
+
+template <bool kFast, int kVariant>
+__device__ __forceinline__ float shape_de(const ShapeDev& s, float px, float py, float pz) {
+    if (kVariant == kVarSphere) return sphere_de(s, px, py, pz);
+    if (kFast) return mandelbulb_de_fast<kVariant == kVarP8>(s, px, py, pz);
+    return mandelbulb_de_exact<kVariant == kVarP8>(s, px, py, pz);
+}
+
+}  // namespace ctc

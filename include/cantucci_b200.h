@@ -1,0 +1,169 @@
+/*
+ * cantucci_b200.h -- C ABI of the B200-native cantucci hot path.
+ *
+ * The reference (LukasKalbertodt/cantucci, Rust) has no FFI layer; the seam
+ * this library plugs into is the `Shape` trait plus one associated function:
+ *
+ *   trait Shape::min_distance_from / batch_min_distance_from
+ *                                   src/shape/mod.rs:37, :89  (impl src/shape/mandelbulb.rs:59-79)
+ *   MeshBuffer::generate_for_box    src/mesh/buffer.rs:30-42  (called from src/mesh/mod.rs:141-148)
+ *   mesh::Vertex / index buffers    src/mesh/mod.rs:255-261, consumed by src/mesh/view.rs:23-41
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and
+ * returns an int status (the reference panics; the Rust shim in
+ * INTEGRATION.md turns a non-zero status back into a panic).  There is no CPU
+ * fallback: without a CUDA device every call fails with CTC_ERR_CUDA /
+ * CTC_ERR_NO_DEVICE.
+ *
+ * Threading: a ctc_ctx may be used from any thread (Shape: Sync + Send);
+ * calls on one context are serialised by an internal mutex.  Create one
+ * context per worker thread for concurrent submission.
+ */
+#ifndef CANTUCCI_B200_H
+#define CANTUCCI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTC_VERSION 100
+
+#if defined(__GNUC__)
+#define CTC_API __attribute__((visibility("default")))
+#else
+#define CTC_API
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+    CTC_OK = 0,
+    /* the reference's argument asserts: span.start < span.end per axis,
+     * resolution a non-zero power of two (src/mesh/buffer.rs:35-39),
+     * GridTable size >= 2 (src/util/grid.rs:25), max_iters >= 1
+     * (src/shape/mandelbulb.rs:20) */
+    CTC_ERR_INVALID_ARGUMENT = 1,
+    CTC_ERR_CUDA = 2,
+    /* output capacity too small; required totals are still written to
+     * v_off[nspans] / i_off[nspans] so the caller can re-allocate and retry */
+    CTC_ERR_OVERFLOW = 3,
+    /* a lerp factor left [0,1] (NaN/inf distance): the reference's worker
+     * would have panicked at src/math.rs:19 */
+    CTC_ERR_LERP_ASSERT = 4,
+    CTC_ERR_NO_DEVICE = 5,
+};
+
+/* ---- plain-data records ------------------------------------------------ */
+
+/* octree::Span = Range<Point3<f32>> (src/octree/mod.rs:13); Range is not
+ * repr(C), so the shim copies start/end into this. */
+typedef struct { float start[3]; float end[3]; } ctc_span;
+
+/* mesh::Vertex (src/mesh/mod.rs:255-261): #[repr(C)], 28 bytes, no padding. */
+typedef struct { float position[3]; float normal[3]; float distance_from_surface; } ctc_vertex;
+
+enum { CTC_SHAPE_MANDELBULB = 0, CTC_SHAPE_SPHERE = 1 };
+
+/* ctc_shape.flags */
+enum {
+    /* IEEE mul/add/div/sqrt in the reference's evaluation order, no FMA
+     * contraction, glibc's logf algorithm: power-8 distances are bit-identical
+     * to the reference's CPU path. */
+    CTC_MATH_EXACT = 0,
+    /* FMA contraction + MUFU approximations (rsqrt/rcp/lg2).  Distances agree
+     * to <= 1e-5 relative away from the escape boundary; see DESIGN.md. */
+    CTC_MATH_FAST = 1,
+};
+
+/* Mandelbulb<P>{max_iters, bailout} (src/shape/mandelbulb.rs:13-16) or
+ * Sphere{center, radius} (src/shape/sphere.rs:7-10). */
+typedef struct {
+    int32_t  kind;        /* CTC_SHAPE_* */
+    uint32_t power;       /* Mandelbulb's const generic P (u8 in the reference) */
+    uint64_t max_iters;
+    float    bailout;
+    float    center[3];   /* Sphere */
+    float    radius;      /* Sphere */
+    uint32_t flags;       /* CTC_MATH_* */
+} ctc_shape;
+
+/* mesh::buffer::Timings (src/mesh/buffer.rs:398-405): the three pass
+ * durations (device time, CUDA events) and the totals over the call. */
+typedef struct {
+    double   first_ms;    /* pass 1: sample grids            (buffer.rs:77-83)   */
+    double   second_ms;   /* pass 2: classify + vertices     (buffer.rs:113-275) */
+    double   third_ms;    /* pass 3: quads / index emission  (buffer.rs:288-372) */
+    uint64_t vertices;
+    uint64_t faces;       /* indices / 6, as buffer.rs:380 */
+} ctc_timings;
+
+typedef struct ctc_ctx ctc_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+
+CTC_API int ctc_version(void);
+/* Number of CUDA devices, or 0. */
+CTC_API int ctc_device_count(void);
+CTC_API int ctc_ctx_create(int device, ctc_ctx **out);
+CTC_API void ctc_ctx_destroy(ctc_ctx *ctx);
+/* Adopt an external cudaStream_t (e.g. the host framework's current stream);
+ * NULL restores the context's own stream. */
+CTC_API int ctc_ctx_set_stream(ctc_ctx *ctx, void *cuda_stream);
+/* Spans per internal launch group (0 = automatic, sized to keep a group's
+ * sample grids L2-resident). */
+CTC_API int ctc_ctx_set_group_spans(ctc_ctx *ctx, uint32_t spans_per_group);
+CTC_API int ctc_ctx_synchronize(ctc_ctx *ctx);
+/* Human-readable description of the last failure on this context. */
+CTC_API const char *ctc_last_error(const ctc_ctx *ctx);
+/* Kernels launched by this context since creation (all entry points). */
+CTC_API uint64_t ctc_kernel_launches(const ctc_ctx *ctx);
+
+/* ---- Shape::batch_min_distance_from (src/shape/mod.rs:89) ---------------- */
+
+/* xyz: n packed Point3<f32> (12-byte stride); out: n f32.  Host pointers. */
+CTC_API int ctc_de_batch(ctc_ctx *ctx, const ctc_shape *shape, const float *xyz, size_t n, float *out);
+/* Same with device pointers; asynchronous on the context's stream. */
+CTC_API int ctc_de_batch_device(ctc_ctx *ctx, const ctc_shape *shape, const float *d_xyz, size_t n, float *d_out);
+
+/* ---- pass 1 only: sample grids (src/mesh/buffer.rs:64-83) ---------------- */
+
+/* grids: nspans x (R+1)^3 f32, index x*(R+1)^2 + y*(R+1) + z
+ * (src/util/grid.rs:45-48), sampled over the skirt-expanded span.
+ * `spans` is a HOST pointer in both variants (24 bytes per span). */
+CTC_API int ctc_sample_grids(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                     uint32_t resolution, float *grids);
+CTC_API int ctc_sample_grids_device(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                            uint32_t resolution, float *d_grids);
+
+/* ---- MeshBuffer::generate_for_box x nspans (src/mesh/buffer.rs:30-391) ---- */
+
+/* Meshes every span.  Vertices of span s are v[v_off[s] .. v_off[s+1]) and
+ * its indices idx[i_off[s] .. i_off[s+1]); indices are span-local (they
+ * index into the span's own vertex range), ordered exactly as the reference
+ * emits them.  v_off / i_off have nspans+1 entries.  Host pointers.
+ * timings may be NULL. */
+CTC_API int ctc_mesh_spans(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                   uint32_t resolution,
+                   ctc_vertex *v, size_t vcap, uint32_t *idx, size_t icap,
+                   uint64_t *v_off, uint64_t *i_off, ctc_timings *timings);
+
+/* Device-resident variant: d_v / d_idx / d_v_off / d_i_off are device
+ * pointers, `spans` stays a host pointer.  Asynchronous on the context's
+ * stream; the status only covers argument checks and launch errors.  Call
+ * ctc_mesh_result() afterwards to synchronise and fetch totals, overflow and
+ * lerp-assert status. */
+CTC_API int ctc_mesh_spans_device(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                          uint32_t resolution,
+                          ctc_vertex *d_v, size_t vcap, uint32_t *d_idx, size_t icap,
+                          uint64_t *d_v_off, uint64_t *d_i_off);
+/* Synchronises the stream and reports the last ctc_mesh_spans_device call:
+ * total vertices / indices REQUIRED (even on overflow), pass timings.
+ * Returns CTC_OK, CTC_ERR_OVERFLOW or CTC_ERR_LERP_ASSERT. */
+CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indices, ctc_timings *timings);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANTUCCI_B200_H */

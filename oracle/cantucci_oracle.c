@@ -343,6 +343,31 @@ int orc_sample_grid(const orc_shape *s, const orc_span *span, uint32_t resolutio
     return 0;
 }
 
+/* per-sample completed-iteration counts (divergence studies, flop accounting) */
+int orc_sample_grid_iters(const orc_shape *s, const orc_span *span, uint32_t resolution,
+                          float *out, uint8_t *iters_out) {
+    if (check_args(span, resolution)) return 1;
+    orc_span ex;
+    expand_span(span, resolution, &ex);
+    float across[3];
+    for (int c = 0; c < 3; c++) across[c] = ex.end[c] - ex.start[c];
+    const uint32_t n = resolution + 1;
+    const float fr = (float)resolution;
+    size_t o = 0;
+    for (uint32_t x = 0; x < n; x++)
+        for (uint32_t y = 0; y < n; y++)
+            for (uint32_t z = 0; z < n; z++) {
+                float v[3] = { (float)x / fr, (float)y / fr, (float)z / fr };
+                float p[3];
+                for (int c = 0; c < 3; c++) p[c] = ex.start[c] + across[c] * v[c];
+                orc_de_info info;
+                out[o] = orc_min_distance_from_info(s, p, &info);
+                iters_out[o] = info.iters > 255 ? 255 : (uint8_t)info.iters;
+                o++;
+            }
+    return 0;
+}
+
 int orc_sample_grid_info(const orc_shape *s, const orc_span *span, uint32_t resolution,
                          float *out, uint64_t *iter_hist, uint64_t *n_bailed) {
     if (check_args(span, resolution)) return 1;

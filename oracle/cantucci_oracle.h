@@ -82,6 +82,9 @@ int  orc_sample_grid(const orc_shape *s, const orc_span *span, uint32_t resoluti
 int  orc_sample_grid_info(const orc_shape *s, const orc_span *span, uint32_t resolution,
                           float *out, uint64_t *iter_hist /* max_iters+1 */, uint64_t *n_bailed);
 
+int  orc_sample_grid_iters(const orc_shape *s, const orc_span *span, uint32_t resolution,
+                           float *out, uint8_t *iters_out);
+
 /* MeshBuffer::generate_for_box (src/mesh/buffer.rs:30-42). Returns 0 ok,
  * 1 = assertion on arguments would fire. out must be released with orc_mesh_free. */
 int  orc_generate_for_box(const orc_shape *s, const orc_span *span, uint32_t resolution, orc_mesh *out);

@@ -100,6 +100,8 @@ def lib() -> C.CDLL:
         L.orc_sample_grid_info.restype = C.c_int
         L.orc_sample_grid_info.argtypes = [C.POINTER(Shape), C.POINTER(Span), C.c_uint32, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
+        L.orc_sample_grid_iters.restype = C.c_int
+        L.orc_sample_grid_iters.argtypes = [C.POINTER(Shape), C.POINTER(Span), C.c_uint32, C.c_void_p, C.c_void_p]
         L.orc_generate_for_box.restype = C.c_int
         L.orc_generate_for_box.argtypes = [C.POINTER(Shape), C.POINTER(Span), C.c_uint32, C.POINTER(Mesh)]
         L.orc_mesh_free.restype = None
@@ -199,6 +201,17 @@ def sample_grid(shape: Shape, span: Span, resolution: int, with_info: bool = Fal
     if rc:
         raise AssertionError("generate_for_box argument assertion (buffer.rs:35-39)")
     return out
+
+
+def sample_grid_iters(shape: Shape, span: Span, resolution: int):
+    """-> (distances, completed iterations per sample [u8, saturating])."""
+    n = resolution + 1
+    out = np.empty(n * n * n, dtype=np.float32)
+    it = np.empty(n * n * n, dtype=np.uint8)
+    rc = lib().orc_sample_grid_iters(C.byref(shape), C.byref(span), resolution, out.ctypes.data, it.ctypes.data)
+    if rc:
+        raise AssertionError("generate_for_box argument assertion (buffer.rs:35-39)")
+    return out, it
 
 
 def _mesh_out(m: Mesh):

@@ -1,0 +1,64 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+# BENCH_POINTS (/root/reference/src/shape/mod.rs:110-133): the reference's only fixture
+# for this path -- inputs only, it stores no expected outputs.
+BENCH_POINTS = np.array([
+    [-0.73772496, -0.002343091, -0.7382717],
+    [-0.7484558, -0.8255949, -0.0026540023],
+    [-1.0951594, -0.0014639703, -0.0027306266],
+    [-0.60622436, -0.16786861, 0.7227598],
+    [-0.6000897, -0.5997089, 0.028461732],
+    [-0.6077231, -0.8336551, -0.004541016],
+    [-0.05153041, -0.5906257, -0.7647207],
+    [-0.73772484, -0.0030531297, -0.7382715],
+    [-1.09658, -0.032518614, 0.026089936],
+    [-0.74845594, -0.8255949, -0.0033077204],
+    [-0.0031473506, 0.59545904, 0.7711717],
+    [0.59178185, -0.009300065, 0.70574695],
+    [0.5934337, -0.0065053166, -0.8548532],
+    [0.5906368, 0.5906708, 0.0002929632],
+    [0.5909915, 0.6001409, -0.4285654],
+    [-0.004541016, 0.5956404, 0.36293367],
+    [-0.00073693885, 0.5916996, -0.8447121],
+    [0.59545904, -0.004541016, 0.35817686],
+    [0.59545904, -0.004541016, -0.3581769],
+    [0.60028464, -0.36826742, 0.6579103],
+], dtype=np.float32)
+
+
+@pytest.fixture(scope="session")
+def bench_points():
+    return BENCH_POINTS.copy()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import cantucci_b200 as cb
+    return cb.default_context(0)
+
+
+def startup_leaves():
+    """The 64 startup leaves (mesh/mod.rs:52-56) in iter_mut order, as [64,6] f32."""
+    import cantucci_b200 as cb
+    tree = cb.startup_tree(cb.Span((-1.2, -1.2, -1.2), (1.2, 1.2, 1.2)))
+    return cb.spans_array([n.span for n in tree.leaves()])
