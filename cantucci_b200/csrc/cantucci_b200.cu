@@ -63,7 +63,7 @@ struct ctc_ctx {
     bool timing = true;
 
     // workspace
-    DevBuf geom, grids, m_active, m_ex, m_ey, m_ez, m_neg, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
+    DevBuf geom, grids, sign_bits, m_active, m_ex, m_ey, m_ez, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
     DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
     DevBuf pts_in, pts_out;
     PinnedBuf h_geom, h_state;
@@ -99,6 +99,7 @@ int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
         d.power = s->power;
         d.max_iters = s->max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s->max_iters;
         d.bailout = s->bailout;
+        { volatile float b2 = s->bailout * s->bailout; d.bail2 = b2; }
     } else if (s->kind == CTC_SHAPE_SPHERE) {
         d.cx = s->center[0]; d.cy = s->center[1]; d.cz = s->center[2]; d.radius = s->radius;
     } else {
@@ -198,9 +199,14 @@ struct PassTimer {
 
 template <bool kFast, int kVariant>
 void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint32_t R, uint32_t lg, float* grids,
-                   size_t stride, uint32_t nspans, size_t n3) {
-    dim3 grid((unsigned)((n3 + kThreads - 1) / kThreads), nspans);
-    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, grids, stride);
+                   size_t stride, uint32_t nspans, size_t n3, uint32_t* sign_bits, uint32_t sign_stride) {
+    // R >= 32: the R^3 core goes to the warp-per-2x4x32-block path (2048 samples per CTA)
+    const size_t R3 = (size_t)R * R * R;
+    const uint32_t core_blocks = lg >= 5 ? (uint32_t)(R3 / (8 * kThreads)) : 0u;
+    const size_t rest = core_blocks ? n3 - R3 : n3;
+    dim3 grid(core_blocks + (unsigned)((rest + kThreads - 1) / kThreads), nspans);
+    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, grids, stride,
+                                                                             sign_bits, sign_stride, core_blocks);
     ctx->launches++;
 }
 
@@ -242,7 +248,7 @@ int sample_grids_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* span
     const int variant = shape_variant(shape);
     for (size_t s0 = 0; s0 < nspans; s0 += 32768) {
         const uint32_t cnt = (uint32_t)((nspans - s0) < 32768 ? (nspans - s0) : 32768);
-#define CALL(F, V) launch_sample<F, V>(ctx, sh, ctx->geom.as<SpanGeom>() + s0, R, lg, d_grids + s0 * n3, n3, cnt, n3)
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, ctx->geom.as<SpanGeom>() + s0, R, lg, d_grids + s0 * n3, n3, cnt, n3, nullptr, 0u)
         DISPATCH(fast, variant, CALL);
 #undef CALL
     }
@@ -308,12 +314,14 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     const uint32_t cell_cap = (uint32_t)(group_cells < vcap ? group_cells : (vcap < 0xFFFFFFFFull ? vcap : 0xFFFFFFFFull));
     CK(ctx->grids.ensure(G * gp.n3 * sizeof(float)));
     CK(ctx->m_active.ensure(words * 4)); CK(ctx->m_ex.ensure(words * 4)); CK(ctx->m_ey.ensure(words * 4));
-    CK(ctx->m_ez.ensure(words * 4)); CK(ctx->m_neg.ensure(words * 4));
+    CK(ctx->m_ez.ensure(words * 4));
+    const uint32_t sign_stride = (uint32_t)((gp.n3 + 31) / 32 + 1);
+    CK(ctx->sign_bits.ensure(G * (size_t)sign_stride * 4));
+    uint32_t* sign_bits = ctx->sign_bits.as<uint32_t>();
     CK(ctx->word_vpre.ensure(words * 4)); CK(ctx->word_qpre.ensure(words * 4));
     CK(ctx->chunk_counts.ensure(chunks * sizeof(uint2))); CK(ctx->chunk_pre.ensure(chunks * sizeof(uint2)));
     CK(ctx->cell_of.ensure((size_t)(cell_cap ? cell_cap : 1) * 4));
-    Masks m{ctx->m_active.as<uint32_t>(), ctx->m_ex.as<uint32_t>(), ctx->m_ey.as<uint32_t>(),
-            ctx->m_ez.as<uint32_t>(), ctx->m_neg.as<uint32_t>()};
+    Masks m{ctx->m_active.as<uint32_t>(), ctx->m_ex.as<uint32_t>(), ctx->m_ey.as<uint32_t>(), ctx->m_ez.as<uint32_t>()};
 
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
     const int variant = shape_variant(shape);
@@ -325,15 +333,16 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
         {   // pass 1
             PassTimer t(ctx, 0);
-#define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3)
+            CK(cudaMemsetAsync(sign_bits, 0, (size_t)cnt * sign_stride * 4, ctx->stream));
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3, sign_bits, sign_stride)
             DISPATCH(fast, variant, CALL);
 #undef CALL
         }
         dim3 cgrid(gp.chunks_per_span, cnt);
         {   // pass 2: classify, scan, vertices
             PassTimer t(ctx, 1);
-            classify_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(grids, gp.n3, R, lg, gp.words_per_span, gp.chunk_words, m,
-                                                                ctx->chunk_counts.as<uint2>());
+            classify_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
+                                                                gp.chunk_words, m, ctx->chunk_counts.as<uint2>());
             scan_chunks_kernel<<<1, kScanThreads, 0, ctx->stream>>>(
                 ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
                 (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
@@ -350,8 +359,8 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         }
         {   // pass 3
             PassTimer t(ctx, 2);
-            quad_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(), R,
-                                                            lg, gp.words_per_span, gp.chunk_words, st, d_idx,
+            quad_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
+                                                            grids, gp.n3, R, lg, gp.words_per_span, gp.chunk_words, st, d_idx,
                                                             (unsigned long long)icap);
             ctx->launches++;
         }
@@ -425,7 +434,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->m_ex, &c->m_ey, &c->m_ez, &c->m_neg, &c->chunk_counts,
+    for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->m_ex, &c->m_ey, &c->m_ez, &c->sign_bits, &c->chunk_counts,
                       &c->chunk_pre, &c->word_vpre, &c->word_qpre, &c->cell_of, &c->state, &c->out_v, &c->out_idx,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out})
         b->release();

@@ -24,6 +24,7 @@ struct ShapeDev {
     uint32_t power;
     uint32_t max_iters;  // clamped to 2^32-1 on the host
     float    bailout;
+    float    bail2;      // bailout * bailout (host, IEEE): the FAST path tests squared radii
     float    cx, cy, cz, radius;
 };
 
@@ -200,6 +201,7 @@ __device__ __forceinline__ float mandelbulb_de_exact(const ShapeDev& s, float px
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float fast_rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float fast_sqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float fast_lg2(float a) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 
 // (a + i b)^n by binary exponentiation, n >= 1 warp-uniform
@@ -218,78 +220,93 @@ __device__ __forceinline__ void cpow(float a, float b, uint32_t n, float& re, fl
     re = rr; im = ri;
 }
 
+// One power-8 step of the FAST path.  Same map as rotate_inner_p8_scalar, but
+//  * the azimuth polynomial is evaluated on the unit vector (u,v) = (x,y)/w, so there is no
+//    division by w^8 (which underflows near the z axis and would inject inf/NaN):
+//        X = A c8,  Y = A s8,  A = z8 - 28 z6 w2 + 70 z4 w4 - 28 z2 w6 + w8,
+//        c8 = u8 - 28 u6 v2 + 70 u4 v4 - 28 u2 v6 - v8   [sic: -v8, as the reference's -y8]
+//        s8 = 8 u v (u6 - 7 u4 v2 + 7 u2 v4 - v6)
+//  * the quartics in (a,b) = (u2,v2) / (z2,w2) are factored:
+//        a4 - 28 a3 b + 70 a2 b2 - 28 a b3 - b4 = S (D - 28 m) + 70 m^2
+//        a4 - 28 a3 b + 70 a2 b2 - 28 a b3 + b4 = S (S - 28 m) + 68 m^2
+//        a3 - 7 a2 b + 7 a b2 - b3            = (a - b)(S - 6 m)
+//    with S = a2 + b2, D = a2 - b2, m = a b.
+// ~46 FMA-pipe instructions + 2 MUFU per iteration against 75 algorithmic flops.
+// w2 is clamped away from zero before the rsqrt, so the step is finite for every finite input.
+__device__ __forceinline__ void rotate_p8_fast(float x, float y, float z, float z2, float w2,
+                                               float px, float py, float pz, float& ox, float& oy, float& oz) {
+    const float iw = fast_rsqrt(fmaxf(w2, 1e-36f));
+    const float w = w2 * iw;
+    const float u = x * iw, v = y * iw;
+    // elevation part
+    const float z4 = z2 * z2, w4 = w2 * w2;
+    const float S1 = z4 + w4, m1 = z2 * w2;
+    const float A = fmaf(68.0f, m1 * m1, S1 * fmaf(-28.0f, m1, S1));
+    const float Zp = (z * w) * (z2 - w2) * fmaf(-6.0f, m1, S1);
+    // azimuth part on the unit circle
+    const float u2 = u * u, v2 = v * v;
+    const float u4 = u2 * u2, v4 = v2 * v2;
+    const float S2 = u4 + v4, D2 = u4 - v4, m2 = u2 * v2;
+    const float c8 = fmaf(70.0f, m2 * m2, S2 * fmaf(-28.0f, m2, D2));
+    const float s8 = (u * v) * (u2 - v2) * fmaf(-6.0f, m2, S2);
+    ox = fmaf(A, c8, px);
+    oy = fmaf(8.0f * A, s8, py);
+    oz = fmaf(8.0f, Zp, pz);
+}
+
+// FAST path for a sample ON the z axis (px == py == 0 exactly): the orbit never leaves the axis
+// (rotate_on_z_axis, mandelbulb.rs:114-126): z' = |z|^P cos(P theta) + pz with theta in {0, pi},
+// i.e. z' = z^P + pz for even P and the same for odd P (cos(P pi) = -1 flips the sign back).
+// The origin is 0/0 in the reference -> NaN.  Cold: one lattice column per dense grid at most.
+__device__ __noinline__ float mandelbulb_de_fast_on_axis(uint32_t P, uint32_t max_iters, float bailout, float pz) {
+    float zz = pz, dr = 1.0f, r = 0.0f;
+    for (uint32_t it = 0; it < max_iters; ++it) {
+        r = fabsf(zz);
+        if (r > bailout) break;
+        if (r == 0.0f) return __int_as_float(0xFFC00000);
+        float rp1 = 1.0f;
+        { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
+        dr = fmaf((float)P * rp1, dr, 1.0f);
+        const float rp = rp1 * r;
+        zz = ((zz < 0.0f && (P & 1u)) ? -rp : rp) + pz;
+    }
+    return canonical_x86_nan(0.5f * __logf(r) * r / dr);
+}
+
 template <bool kP8>
-__device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px, float py, float pz,
-                                                    uint32_t* iters_out = nullptr) {
+__device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px, float py, float pz) {
     const uint32_t P = kP8 ? 8u : s.power;
-    const float bail2 = s.bailout * s.bailout;
+    if (px == 0.0f && py == 0.0f) return mandelbulb_de_fast_on_axis(P, s.max_iters, s.bailout, pz);
+    const float bail2 = s.bail2;
     float zx = px, zy = py, zz = pz;
     float dr = 1.0f, r2 = 0.0f;
-    uint32_t it = 0;
-    for (; it < s.max_iters; ++it) {
-        const float x2 = zx * zx, y2 = zy * zy, z2 = zz * zz;
-        const float w2 = x2 + y2;
+    for (uint32_t it = 0; it < s.max_iters; ++it) {
+        const float z2 = zz * zz;
+        const float w2 = fmaf(zx, zx, zy * zy);
         r2 = w2 + z2;
         if (r2 > bail2) break;                   // r > bailout, on squares
-        const float r = fast_sqrt(r2);
-        float nx, ny, nz;
         if (kP8) {
+            // dr = 8 r^7 dr + 1
             const float r6 = r2 * r2 * r2;
-            dr = fmaf(8.0f * (r6 * r), dr, 1.0f);
-            if (w2 == 0.0f) {
-                // on the z axis: theta is 0 or pi, cos(8 theta) = 1; origin -> NaN like the reference
-                nx = 0.0f; ny = 0.0f;
-                nz = (r2 == 0.0f) ? __int_as_float(0x7fc00000) : r2 * r6;
-            } else {
-                const float x4 = x2 * x2, y4 = y2 * y2, z4 = z2 * z2, w4 = w2 * w2;
-                const float w6 = w4 * w2, w8 = w4 * w4;
-                // a = 1 + (z8 - 28 z6 w2 + 70 z4 w4 - 28 z2 w6) / w8
-                float t = fmaf(-28.0f * (z4 * z2), w2, z4 * z4);
-                t = fmaf(70.0f * z4, w4, t);
-                t = fmaf(-28.0f * z2, w6, t);
-                const float a = fmaf(t, fast_rcp(w8), 1.0f);
-                // X = a (x8 - 28 x6 y2 + 70 x4 y4 - 28 x2 y6 - y8)   [sic: -y8, as the reference]
-                float qx = fmaf(-28.0f * (x4 * x2), y2, fmaf(x4, x4, -(y4 * y4)));
-                qx = fmaf(70.0f * x4, y4, qx);
-                qx = fmaf(-28.0f * x2, y4 * y2, qx);
-                // Y = 8 a x y (x6 - 7 x4 y2 + 7 x2 y4 - y6)
-                float qy = fmaf(x4, x2, -(y4 * y2));
-                qy = fmaf(-7.0f * x4, y2, qy);
-                qy = fmaf(7.0f * x2, y4, qy);
-                // Z = 8 z sqrt(w2) (z2 - w2)(z4 - 6 z2 w2 + w4)
-                const float qz = fmaf(-6.0f * z2, w2, z4 + w4);
-                nx = a * qx;
-                ny = (8.0f * a) * (zx * zy) * qy;
-                nz = (8.0f * zz) * fast_sqrt(w2) * ((z2 - w2) * qz);
-            }
+            dr = fmaf(8.0f * (r6 * fast_sqrt(r2)), dr, 1.0f);
+            rotate_p8_fast(zx, zy, zz, z2, w2, px, py, pz, zx, zy, zz);
         } else {
+            const float r = fast_sqrt(r2);
             // generic P without trig: (z + i w)^P = r^P (cos P.theta + i sin P.theta),
-            // (x + i y)^P = w^P (cos P.phi + i sin P.phi)
+            // ((x + i y)/w)^P = cos P.phi + i sin P.phi
             float rp1 = 1.0f;                       // r^(P-1)
             { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
             dr = fmaf((float)P * rp1, dr, 1.0f);
-            const float w = fast_sqrt(w2);
-            float ct, st;                           // r^P cos(P theta), r^P sin(P theta)
-            cpow(zz, w, P, ct, st);
-            if (w2 == 0.0f) {
-                nx = 0.0f; ny = 0.0f;
-                nz = (r2 == 0.0f) ? __int_as_float(0x7fc00000) : ct;
-            } else {
-                float cp, sp;                       // w^P cos(P phi), w^P sin(P phi)
-                cpow(zx, zy, P, cp, sp);
-                float wp = 1.0f;                    // w^P
-                { float cur = w; uint32_t n = P; while (n) { if (n & 1u) wp *= cur; n >>= 1; if (n) cur *= cur; } }
-                const float sw = st * fast_rcp(wp);
-                nx = sw * cp; ny = sw * sp; nz = ct;
-            }
+            const float iw = fast_rsqrt(fmaxf(w2, 1e-36f));
+            const float w = w2 * iw;
+            float ct, st, cp, sp;
+            cpow(zz, w, P, ct, st);                 // r^P cos(P theta), r^P sin(P theta)
+            cpow(zx * iw, zy * iw, P, cp, sp);      // cos(P phi), sin(P phi)
+            zx = fmaf(st, cp, px); zy = fmaf(st, sp, py); zz = ct + pz;
         }
-        zx = nx + px; zy = ny + py; zz = nz + pz;
     }
-    if (iters_out) *iters_out = it;
     // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
-    const float r = fast_sqrt(r2);
-    const float out = (0.25f * 0.69314718056f) * fast_lg2(r2) * r * fast_rcp(dr);
-    return canonical_x86_nan(out);
+    return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
 }
 
 // Sphere::min_distance_from (sphere.rs:33-35); cgmath magnitude = sqrt((x*x+y*y)+z*z)

@@ -2,7 +2,9 @@
 //
 //   K1  sample_grids_kernel   pass 1 of naive_surface_nets (mesh/buffer.rs:77-83)
 //   K3  de_batch_kernel       Shape::batch_min_distance_from (shape/mod.rs:89)
-//   E1  classify_kernel       cell / edge sign classification (buffer.rs:116-147, 299-350)
+//       (also emits the sign bit-plane: 1 bit per sample, reference layout)
+//   E1  classify_kernel       cell / edge sign classification from the bit-plane, 32 cells per
+//                             thread (buffer.rs:116-147, 299-350)
 //   E2a scan_chunks_kernel    order-preserving prefix over chunk counts
 //   E2b apply_prefix_kernel   per-word prefixes + compacted active-cell list
 //   E3  vertex_kernel         per-active-cell vertex (buffer.rs:150-274)
@@ -88,25 +90,82 @@ __device__ __forceinline__ void decode_sample(uint32_t i, uint32_t R, uint32_t l
 }
 
 // ---------------------------------------------------------------------------
-// K1: sample grids.  One thread per sample, gridDim.y = spans of the group.
+// K1: sample grids; gridDim.y = spans of the group.
+//
+// Besides the f32 grid the kernel emits the SIGN BIT-PLANE of the grid: bit j of
+// `sign_bits` (per span, j = x*n^2 + y*n + z, the reference's GridTable index)
+// is f32::is_sign_positive() == false.  Everything the mesher decides
+// (buffer.rs:130-147, 194-196, 299-350) is a function of these bits, so the
+// extraction passes never re-read the 4-byte samples except at active cells.
+// The plane must be zeroed before the launch.
+//
+// Blocks [0, core_blocks): the R^3 core for R >= 32.  A warp owns a 2x4x32 block
+// of samples and walks it in 8 steps of one 2x4x4 brick (lane = xl:yl:zl), so
+// iteration counts inside a warp stay coherent, the per-warp set-up (decode,
+// geometry load, x/y position) is paid once per 256 samples, and the 8 ballots
+// assemble the 8 row words of the block's sign bits without shared memory.
+// Remaining blocks: faces / edges / corner (and everything when R < 32), one
+// thread per sample.
 // ---------------------------------------------------------------------------
 template <bool kFast, int kVariant>
 __global__ void __launch_bounds__(kThreads)
 sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r,
-                    float* __restrict__ grids, size_t grid_stride) {
+                    float* __restrict__ grids, size_t grid_stride,
+                    uint32_t* __restrict__ sign_bits, uint32_t sign_stride /* words per span, 0 = no plane */,
+                    uint32_t core_blocks) {
     const uint32_t n = R + 1u;
+    const SpanGeom g = geom[blockIdx.y];
+    float* __restrict__ grid = grids + (size_t)blockIdx.y * grid_stride;
+    uint32_t* __restrict__ plane = sign_bits + (size_t)blockIdx.y * sign_stride;
+    if (blockIdx.x < core_blocks) {
+        const uint32_t lane = threadIdx.x & 31u;
+        const uint32_t wb = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);   // 2x4x32 block id, z fastest
+        const uint32_t zb = wb & ((R >> 5) - 1u);
+        const uint32_t yb = (wb >> (lg - 5)) & ((R >> 2) - 1u);
+        const uint32_t xb = wb >> (2 * lg - 7);
+        const uint32_t x = (xb << 1) | (lane >> 4), y = (yb << 2) | ((lane >> 2) & 3u);
+        uint32_t z = (zb << 5) | (lane & 3u);
+        // v = (x,y,z) as f32 / R  (exact: R is a power of two);  p = start + across * v  (buffer.rs:79-80)
+        const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
+        const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
+        float vz = __fmul_rn((float)z, inv_r);
+        const float dvz = 4.0f * inv_r;                 // exact increments: multiples of 1/R in [0,1]
+        float* out = grid + ((size_t)x * n + y) * n + z;                         // util/grid.rs:45-48
+        uint32_t row_shift = (lane >> 2) << 2;          // this lane's row (xl,yl) nibble in a brick ballot
+        asm volatile("" : "+r"(row_shift));             // keep it in a register (no S2R re-read per step)
+        const float gs2 = g.s[2], ga2 = g.across[2];
+        uint32_t word = 0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));
+            const float d = shape_de<kFast, kVariant>(sh, px, py, pz);
+            *out = d;
+            out += 4;
+            const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);
+            word = __funnelshift_r(word, b >> row_shift, 4);   // nibble j ends up at bits [4j, 4j+4)
+            vz = __fadd_rn(vz, dvz);
+        }
+        if (sign_stride != 0u && (lane & 3u) == 0u && word != 0u) {
+            const uint32_t j0 = (x * n + y) * n + (zb << 5);
+            const uint32_t sft = j0 & 31u;
+            atomicOr(&plane[j0 >> 5], word << sft);
+            if (sft) atomicOr(&plane[(j0 >> 5) + 1u], word >> (32u - sft));
+        }
+        return;
+    }
     const uint32_t n3 = n * n * n;
-    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t R3 = R << (2 * lg);
+    const uint32_t i = (blockIdx.x - core_blocks) * kThreads + threadIdx.x + (core_blocks ? R3 : 0u);
     if (i >= n3) return;
     uint32_t x, y, z;
     decode_sample(i, R, lg, x, y, z);
-    const SpanGeom g = geom[blockIdx.y];
-    // v = (x,y,z) as f32 / R  (exact: R is a power of two);  p = start + across * v  (buffer.rs:79-80)
     const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
     const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
     const float pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));
     const float d = shape_de<kFast, kVariant>(sh, px, py, pz);
-    grids[(size_t)blockIdx.y * grid_stride + ((size_t)x * n + y) * n + z] = d;   // util/grid.rs:45-48
+    const uint32_t j = (x * n + y) * n + z;
+    grid[j] = d;
+    if (sign_stride != 0u && (__float_as_uint(d) >> 31)) atomicOr(&plane[j >> 5], 1u << (j & 31u));
 }
 
 // ---------------------------------------------------------------------------
@@ -151,64 +210,90 @@ __device__ __forceinline__ void block_exclusive_scan2(uint32_t v, uint32_t q, ui
 }
 
 // ---------------------------------------------------------------------------
-// E1: classification.  One CTA per chunk of <= 256 words (32 cells per word,
-// cube(R) order).  gridDim = (chunks_per_span, spans).
+// E1: classification from the sign bit-plane.  One thread per word of 32 cells
+// (cube(R) order), one CTA per chunk of <= 256 words; gridDim = (chunks_per_span,
+// spans).  For R >= 32 a word is 32 z-consecutive cells of one (x,y) row: its 8
+// corner sign words are 33-bit windows of four plane rows (funnel shifts), and
+// the active / edge masks are a handful of bitwise ops.
 // ---------------------------------------------------------------------------
 struct Masks {
     uint32_t* active;  // cell crosses the surface (buffer.rs:130-141)
     uint32_t* ex;      // +x edge from the cell's lower corner emits a quad (:302)
     uint32_t* ey;      // +y edge (:326)
     uint32_t* ez;      // +z edge (:350)
-    uint32_t* neg;     // dists[(x,y,z)] < 0.0 (winding, :310)
 };
 
+__device__ __forceinline__ uint32_t plane_bit(const uint32_t* __restrict__ plane, uint32_t j) {
+    return (plane[j >> 5] >> (j & 31u)) & 1u;
+}
+
+// 33 consecutive plane bits starting at j: lo = bits j..j+31, returns bit j+32 in hi
+__device__ __forceinline__ uint32_t plane_window(const uint32_t* __restrict__ plane, uint32_t j, uint32_t& hi) {
+    const uint32_t w0 = plane[j >> 5], w1 = plane[(j >> 5) + 1u];
+    const uint32_t s = j & 31u;
+    hi = (w1 >> s) & 1u;
+    return __funnelshift_r(w0, w1, s);
+}
+
 __global__ void __launch_bounds__(kThreads)
-classify_kernel(const float* __restrict__ grids, size_t grid_stride, uint32_t R, uint32_t lg,
+classify_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, uint32_t R, uint32_t lg,
                 uint32_t words_per_span, uint32_t chunk_words, Masks m, uint2* __restrict__ chunk_counts) {
     const uint32_t span = blockIdx.y, chunk = blockIdx.x;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t t = threadIdx.x;
     const uint32_t n = R + 1u, R3 = R << (2 * lg);
-    const float* __restrict__ g = grids + (size_t)span * grid_stride;
-    uint32_t vcnt = 0, qcnt = 0;
-    for (uint32_t w = warp; w < chunk_words; w += kThreads / 32) {
-        const uint32_t word = chunk * chunk_words + w;
-        const uint32_t c = (word << 5) | lane;
-        bool act = false, fx = false, fy = false, fz = false, ng = false;
-        if (c < R3) {
-            const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
-            const float* p = g + ((size_t)x * n + y) * n + z;
-            const size_t sy = n, sx = (size_t)n * n;
-            // corner id = 4*dx + 2*dy + dz (buffer.rs:116-125)
-            const float d0 = p[0], d1 = p[1], d2 = p[sy], d3 = p[sy + 1];
-            const float d4 = p[sx], d5 = p[sx + 1], d6 = p[sx + sy], d7 = p[sx + sy + 1];
-            const uint32_t s0 = __float_as_uint(d0) >> 31;
-            const uint32_t s1 = __float_as_uint(d1) >> 31, s2 = __float_as_uint(d2) >> 31;
-            const uint32_t s3 = __float_as_uint(d3) >> 31, s4 = __float_as_uint(d4) >> 31;
-            const uint32_t s5 = __float_as_uint(d5) >> 31, s6 = __float_as_uint(d6) >> 31;
-            const uint32_t s7 = __float_as_uint(d7) >> 31;
-            const uint32_t sum = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
-            act = (sum != 0u) && (sum != 8u);
-            fx = (y > 0u) && (z > 0u) && (s0 != s4);
-            fy = (x > 0u) && (z > 0u) && (s0 != s2);
-            fz = (x > 0u) && (y > 0u) && (s0 != s1);
-            ng = d0 < 0.0f;
+    const uint32_t* __restrict__ plane = sign_bits + (size_t)span * sign_stride;
+    uint32_t ma = 0, mx = 0, my = 0, mz = 0;
+    if (t < chunk_words) {
+        const uint32_t word = chunk * chunk_words + t;
+        const uint32_t c0 = word << 5;
+        if (lg >= 5) {
+            const uint32_t x = c0 >> (2 * lg), y = (c0 >> lg) & (R - 1u), z0 = c0 & (R - 1u);
+            const uint32_t j = (x * n + y) * n + z0;
+            uint32_t h0, h2, h4, h6;
+            const uint32_t s0 = plane_window(plane, j, h0);                 // corner 0 (x, y, z)
+            const uint32_t s2 = plane_window(plane, j + n, h2);             // corner 2 (x, y+1, z)
+            const uint32_t s4 = plane_window(plane, j + n * n, h4);         // corner 4 (x+1, y, z)
+            const uint32_t s6 = plane_window(plane, j + n * n + n, h6);     // corner 6 (x+1, y+1, z)
+            const uint32_t s1 = (s0 >> 1) | (h0 << 31), s3 = (s2 >> 1) | (h2 << 31);   // dz = 1 corners
+            const uint32_t s5 = (s4 >> 1) | (h4 << 31), s7 = (s6 >> 1) | (h6 << 31);
+            const uint32_t any = s0 | s1 | s2 | s3 | s4 | s5 | s6 | s7;
+            const uint32_t all = s0 & s1 & s2 & s3 & s4 & s5 & s6 & s7;
+            ma = any & ~all;
+            const uint32_t zm = z0 == 0u ? ~1u : ~0u;                       // z > 0
+            mx = (y > 0u) ? ((s0 ^ s4) & zm) : 0u;                          // y > 0 && z > 0 (:302)
+            my = (x > 0u) ? ((s0 ^ s2) & zm) : 0u;                          // x > 0 && z > 0 (:326)
+            mz = (x > 0u && y > 0u) ? (s0 ^ s1) : 0u;                       // x > 0 && y > 0 (:350)
+        } else {
+            for (uint32_t b = 0; b < 32u; ++b) {
+                const uint32_t c = c0 + b;
+                if (c >= R3) break;
+                const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
+                const uint32_t j = (x * n + y) * n + z;
+                const uint32_t s0 = plane_bit(plane, j), s1 = plane_bit(plane, j + 1u);
+                const uint32_t s2 = plane_bit(plane, j + n), s3 = plane_bit(plane, j + n + 1u);
+                const uint32_t s4 = plane_bit(plane, j + n * n), s5 = plane_bit(plane, j + n * n + 1u);
+                const uint32_t s6 = plane_bit(plane, j + n * n + n), s7 = plane_bit(plane, j + n * n + n + 1u);
+                const uint32_t sum = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
+                ma |= (uint32_t)(sum != 0u && sum != 8u) << b;
+                mx |= (uint32_t)(y > 0u && z > 0u && s0 != s4) << b;
+                my |= (uint32_t)(x > 0u && z > 0u && s0 != s2) << b;
+                mz |= (uint32_t)(x > 0u && y > 0u && s0 != s1) << b;
+            }
         }
-        const uint32_t ba = __ballot_sync(0xffffffffu, act);
-        const uint32_t bx = __ballot_sync(0xffffffffu, fx);
-        const uint32_t by = __ballot_sync(0xffffffffu, fy);
-        const uint32_t bz = __ballot_sync(0xffffffffu, fz);
-        const uint32_t bn = __ballot_sync(0xffffffffu, ng);
-        if (lane == 0u) {
-            const size_t o = (size_t)span * words_per_span + word;
-            m.active[o] = ba; m.ex[o] = bx; m.ey[o] = by; m.ez[o] = bz; m.neg[o] = bn;
-        }
-        vcnt += __popc(ba);
-        qcnt += __popc(bx) + __popc(by) + __popc(bz);
+        const size_t o = (size_t)span * words_per_span + word;
+        m.active[o] = ma; m.ex[o] = mx; m.ey[o] = my; m.ez[o] = mz;
+    }
+    // chunk totals
+    uint32_t v = __popc(ma), q = __popc(mx) + __popc(my) + __popc(mz);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
     }
     __shared__ uint32_t sv[kThreads / 32], sq[kThreads / 32];
-    if (lane == 0u) { sv[warp] = vcnt; sq[warp] = qcnt; }
+    if ((t & 31u) == 0u) { sv[t >> 5] = v; sq[t >> 5] = q; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (t == 0) {
         uint32_t tv = 0, tq = 0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) { tv += sv[w]; tq += sq[w]; }
@@ -391,7 +476,8 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
 }
 
 // ---------------------------------------------------------------------------
-// E4: quads.  Same grid as E1 (thread per cell == per lower corner).
+// E4: quads.  One thread per word of 32 lower corners (same grid as E1); the
+// ~85% of words without a sign-changing edge leave after three loads.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t vertex_id(const uint32_t* __restrict__ active, const uint32_t* __restrict__ word_vpre,
                                               size_t span_w0, uint32_t c) {
@@ -399,59 +485,49 @@ __device__ __forceinline__ uint32_t vertex_id(const uint32_t* __restrict__ activ
     return word_vpre[o] + __popc(active[o] & ((1u << (c & 31u)) - 1u));
 }
 
+__device__ __forceinline__ void store_quad(uint32_t* __restrict__ out_idx, unsigned long long q, unsigned long long icap,
+                                           bool flip, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    if (6ull * q + 6ull > icap) return;
+    uint2* d = reinterpret_cast<uint2*>(out_idx + 6ull * q);
+    if (flip) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }   // [v0,v2,v1, v1,v2,v3]
+    else      { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }   // [v0,v1,v2, v1,v3,v2]
+}
+
 __global__ void __launch_bounds__(kThreads)
 quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __restrict__ word_qpre,
+            const float* __restrict__ grids, size_t grid_stride,
             uint32_t R, uint32_t lg, uint32_t words_per_span, uint32_t chunk_words,
             const MeshState* __restrict__ st, uint32_t* __restrict__ out_idx, unsigned long long icap) {
     const uint32_t span = blockIdx.y, chunk = blockIdx.x;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned long long base_q = st->group_base_q;
+    if (threadIdx.x >= chunk_words) return;
+    const uint32_t word = chunk * chunk_words + threadIdx.x;
     const size_t w0 = (size_t)span * words_per_span;
-    const uint32_t R2 = R << lg;
-    for (uint32_t w = warp; w < chunk_words; w += kThreads / 32) {
-        const uint32_t word = chunk * chunk_words + w;
-        const size_t o = w0 + word;
-        const uint32_t bx = m.ex[o], by = m.ey[o], bz = m.ez[o];
-        if ((bx | by | bz) == 0u) continue;
-        const uint32_t bit = 1u << lane, lt = bit - 1u;
-        const uint32_t hx = (bx >> lane) & 1u, hy = (by >> lane) & 1u, hz = (bz >> lane) & 1u;
-        if ((hx | hy | hz) == 0u) continue;
-        const bool neg = (m.neg[o] >> lane) & 1u;
-        const uint32_t c = (word << 5) | lane;
-        // quads before this corner within the word, in corner order
-        unsigned long long q = base_q + word_qpre[o] + __popc(bx & lt) + __popc(by & lt) + __popc(bz & lt);
+    const size_t o = w0 + word;
+    const uint32_t bx = m.ex[o], by = m.ey[o], bz = m.ez[o];
+    uint32_t todo = bx | by | bz;
+    if (todo == 0u) return;
+    const uint32_t n = R + 1u, R2 = R << lg;
+    const float* __restrict__ g = grids + (size_t)span * grid_stride;
+    unsigned long long q = st->group_base_q + word_qpre[o];
+    while (todo) {
+        const uint32_t b = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t c = (word << 5) | b;
+        const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
+        // winding uses `dists[(x,y,z)] < 0.0`, not the sign bit (buffer.rs:310): -0.0 and NaN differ
+        const bool neg = g[((size_t)x * n + y) * n + z] < 0.0f;
         const uint32_t v3 = vertex_id(m.active, word_vpre, w0, c);
-        if (hx) {   // buffer.rs:302-323
-            const uint32_t v0 = vertex_id(m.active, word_vpre, w0, c - R - 1u);
-            const uint32_t v1 = vertex_id(m.active, word_vpre, w0, c - R);
-            const uint32_t v2 = vertex_id(m.active, word_vpre, w0, c - 1u);
-            if (6ull * q + 6ull <= icap) {
-                uint2* d = reinterpret_cast<uint2*>(out_idx + 6ull * q);
-                if (neg) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }
-                else     { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }
-            }
-            ++q;
+        if ((bx >> b) & 1u) {   // +x edge, buffer.rs:302-323
+            store_quad(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R - 1u),
+                       vertex_id(m.active, word_vpre, w0, c - R), vertex_id(m.active, word_vpre, w0, c - 1u), v3);
         }
-        if (hy) {   // buffer.rs:326-347 (winding flipped relative to x/z)
-            const uint32_t v0 = vertex_id(m.active, word_vpre, w0, c - R2 - 1u);
-            const uint32_t v1 = vertex_id(m.active, word_vpre, w0, c - R2);
-            const uint32_t v2 = vertex_id(m.active, word_vpre, w0, c - 1u);
-            if (6ull * q + 6ull <= icap) {
-                uint2* d = reinterpret_cast<uint2*>(out_idx + 6ull * q);
-                if (neg) { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }
-                else     { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }
-            }
-            ++q;
+        if ((by >> b) & 1u) {   // +y edge, buffer.rs:326-347 (winding flipped relative to x/z)
+            store_quad(out_idx, q++, icap, !neg, vertex_id(m.active, word_vpre, w0, c - R2 - 1u),
+                       vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - 1u), v3);
         }
-        if (hz) {   // buffer.rs:350-371
-            const uint32_t v0 = vertex_id(m.active, word_vpre, w0, c - R2 - R);
-            const uint32_t v1 = vertex_id(m.active, word_vpre, w0, c - R2);
-            const uint32_t v2 = vertex_id(m.active, word_vpre, w0, c - R);
-            if (6ull * q + 6ull <= icap) {
-                uint2* d = reinterpret_cast<uint2*>(out_idx + 6ull * q);
-                if (neg) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }
-                else     { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }
-            }
+        if ((bz >> b) & 1u) {   // +z edge, buffer.rs:350-371
+            store_quad(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R2 - R),
+                       vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - R), v3);
         }
     }
 }
