@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json metric) on B200.
+
+Workload (config.workload): the Mandelbulb power-8 volume over its bounding box
+at 1024^3 cells, stated the way the reference scales resolution -- 16^3 octree
+spans of RESOLUTION = 64 (65^3 samples each, 4096 spans) -- Mandelbulb::classic(6, 2.5).
+One step = evaluate every span's DE sample grid AND extract every span's
+surface-nets mesh (all three passes of naive_surface_nets); with N > 1 GPUs the
+spans are sharded over the ranks and the vertex/index buffers gathered to rank 0
+(strong scaling: total work fixed).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference ...                     the CPU oracle (port of the reference's
+                                                           CPU path), all host threads, bounded sample
+
+Prints ONE JSON line (see the task contract): metric = DE samples/s of the whole
+step (samples evaluated in pass 1 / step time), plus `e2e`, `roofline`,
+`cpu_baseline`, `clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mandelbulb_de_samples_per_s"
+UNIT = "samples/s"
+TILES = 16          # 16^3 spans
+RES = 64            # RESOLUTION (mesh/mod.rs:133)
+POWER, MAX_ITERS, BAILOUT = 8, 6, 2.5      # Mandelbulb::classic(6, 2.5) (app.rs:105)
+WORKLOAD = "mandelbulb_p8_i6_b2.5_bbox_1024cube_as_16x16x16_spans_R64"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def workload_spans(tiles=TILES):
+    import cantucci_b200 as cb
+    return cb.tile_volume(cb.Span((-1.2, -1.2, -1.2), (1.2, 1.2, 1.2)), tiles)
+
+
+def read_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        # "under load": samples whose power draw is in the upper half of what was seen
+        if sm:
+            thr = 0.5 * (min(power) + max(power)) if power else 0
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                    "samples": len(sm), "power_w_max": max(power) if power else None}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle (CPU port of the reference's path)
+# ---------------------------------------------------------------------------
+def cpu_sample_spans(spans: np.ndarray, stride: int) -> np.ndarray:
+    """A bounded, representative sample of the workload: the tiles with (ix + 3 iy + 5 iz) % stride == 0,
+    i.e. 1/stride of the spans spread evenly through the volume (interior, surface and empty
+    spans in their true mix)."""
+    t = round(spans.shape[0] ** (1.0 / 3.0))
+    i = np.arange(spans.shape[0])
+    ix, iy, iz = i // (t * t), (i // t) % t, i % t
+    return np.ascontiguousarray(spans[(ix + 3 * iy + 5 * iz) % stride == 0])
+
+
+def run_cpu(spans: np.ndarray, threads: int | None = None):
+    from oracle import oracle as O
+    sh = O.mandelbulb(POWER, MAX_ITERS, BAILOUT)
+    threads = threads or O.hardware_threads()
+    meshes, secs = O.generate_for_boxes_mt(sh, spans, RES, threads)
+    nv = sum(len(m[0]) for m in meshes if m is not None)
+    nq = sum(len(m[1]) // 6 for m in meshes if m is not None)
+    samples = spans.shape[0] * (RES + 1) ** 3
+    return {"secs": secs, "samples": samples, "spans": spans.shape[0], "threads": threads, "vertices": nv, "quads": nq}
+
+
+def reference_main(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    spans = workload_spans()
+    sample = cpu_sample_spans(spans, 16)          # 256 of the 4096 spans per step
+    times = []
+    res = None
+    for s in range(args.warmup + args.steps):
+        res = run_cpu(sample)
+        if s >= args.warmup:
+            times.append(res["secs"])
+    t = float(np.mean(times))
+    value = res["samples"] / t
+    desc = f"{res['spans']} of {spans.shape[0]} spans per step (tiles with (ix+3iy+5iz)%16==0, spread evenly through the volume)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "spans": int(spans.shape[0]), "resolution": RES, "power": POWER,
+                   "max_iters": MAX_ITERS, "bailout": BAILOUT, "cpu_sample": desc},
+        "span_meshes_per_s": res["spans"] / t,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------
+def ours_main(args):
+    import torch
+    import torch.distributed as dist
+    import cantucci_b200 as cb
+    from cantucci_b200 import _lib
+    from cantucci_b200.scheduler import DeviceMesher, SpanScheduler, shard_indices
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    ctx = cb.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    fast = not args.exact
+    shape = cb.Mandelbulb.classic(MAX_ITERS, BAILOUT, fast=fast)
+    sh = shape._ctc_shape()
+    spans = workload_spans(args.tiles)
+    nspans = spans.shape[0]
+    mine = shard_indices(nspans, world, rank)
+    n3 = (RES + 1) ** 3
+    total_samples = nspans * n3
+
+    # capacities from one sizing run of this rank's shard (outside the timed region)
+    probe = DeviceMesher(ctx, torch, device, 1, 6, len(mine))
+    probe.launch(sh, np.ascontiguousarray(spans[mine]), RES)
+    ctx.check(0)
+    nv_req, ni_req = C.c_uint64(0), C.c_uint64(0)
+    _lib.lib().ctc_mesh_result(ctx.handle, C.byref(nv_req), C.byref(ni_req), None)
+    del probe
+    nv_loc, ni_loc = int(nv_req.value), int(ni_req.value)
+    tot = torch.tensor([nv_loc, ni_loc], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(tot)
+    nv_tot, ni_tot = int(tot[0]), int(tot[1])
+    pad = lambda n: int(n * 1.02) + 1024
+    mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
+    sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot))
+
+    def step():
+        return sched.run(sh, spans, RES)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = ctx.kernel_launches()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches1 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms = np.zeros(3)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches2 = ctx.kernel_launches()
+    # pass timings of the last step (CUDA events on the launching stream, inside the timed region)
+    t = _lib.CtcTimings()
+    _lib.lib().ctc_mesh_result(ctx.handle, None, None, C.byref(t))
+    pass_ms[:] = (t.first_ms, t.second_ms, t.third_ms)
+    tms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tms[0]) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = total_samples / (ms_per_step * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = read_peaks()
+        # ---- algorithmic flops of the dominant kernel (pass 1, sample_grids_kernel) -------------
+        stats = (C.c_uint64 * 3)()
+        sub = np.ascontiguousarray(spans[mine])
+        ctx.check(_lib.lib().ctc_iteration_stats(ctx.handle, C.byref(sh), sub.ctypes.data, sub.shape[0], RES, stats))
+        sum_k, n_bailed, n_s = int(stats[0]), int(stats[1]), int(stats[2])
+        flops_pass1 = 75.0 * sum_k + 6.0 * n_bailed + 10.0 * n_s
+        k1_ms = float(pass_ms[0])
+        achieved = flops_pass1 / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        probe_tf, sms = C.c_double(0.0), C.c_int(0)
+        _lib.lib().ctc_fp32_peak_probe(ctx.handle, C.byref(probe_tf), C.byref(sms))
+        nominal = (sms.value or 148) * 128 * 2 * sm_max * 1e6 / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {
+            "bound": "fp32", "kernel": "sample_grids_kernel (pass 1: DE over the span sample grids)",
+            "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal if nominal else None,
+            "traffic": traffic,
+            "peak_source": f"no FP32 figure in MEASURED_PEAKS.json: SMs x 128 lanes x 2 x clocks.max.sm = {sms.value} x 128 x 2 x {sm_max:.0f} MHz",
+            "peak_measured_fma_tflops": probe_tf.value,
+            "frac_of_measured_fma": achieved / probe_tf.value if probe_tf.value else None,
+            "algorithmic_flops_per_launch_group": flops_pass1, "mean_iterations_per_sample": sum_k / max(n_s, 1),
+            "kernel_ms_per_step": k1_ms,
+            "passes_ms_last_step": {"first_de": pass_ms[0], "second_classify_vertices": pass_ms[1], "third_quads": pass_ms[2]},
+            "hbm_gbs_measured": peaks.get("hbm_gbs"),
+        }
+        # ---- e2e: host buffers through the public C ABI call (ctc_mesh_spans), copies included ---
+        e2e = None
+        if world == 1:
+            v_host = torch.empty((pad(nv_tot), 7), dtype=torch.float32).pin_memory()
+            i_host = torch.empty((pad(ni_tot),), dtype=torch.int32).pin_memory()
+            v_off = np.zeros(nspans + 1, dtype=np.uint64); i_off = np.zeros(nspans + 1, dtype=np.uint64)
+            def e2e_step():
+                rc = _lib.lib().ctc_mesh_spans(ctx.handle, C.byref(sh), spans.ctypes.data, nspans, RES,
+                                               v_host.data_ptr(), v_host.shape[0], i_host.data_ptr(), i_host.shape[0],
+                                               v_off.ctypes.data, i_off.ctypes.data, None)
+                ctx.check(rc)
+            for _ in range(max(1, min(args.warmup, 3))):
+                e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_e2e = max(3, min(args.steps, 10))
+            for _ in range(n_e2e):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_e2e
+            nv, ni = int(v_off[nspans]), int(i_off[nspans])
+            e2e = {"value": total_samples / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": int(nspans * 48),
+                   "d2h_bytes_per_step": int(nv * 28 + ni * 4 + 2 * (nspans + 1) * 8 + 48),
+                   "api": "ctc_mesh_spans (host pointers; pinned host buffers)", "steps": n_e2e}
+        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            sample = cpu_sample_spans(spans, 16 if args.tiles >= 16 else 4)
+            r = run_cpu(sample)
+            cpu = {"value": r["samples"] / r["secs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                   "sample": f"{r['spans']} of {nspans} spans (tiles with (ix+3iy+5iz)%stride==0), {r['secs']:.2f} s",
+                   "span_meshes_per_s": r["spans"] / r["secs"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.tiles == TILES else f"bbox_as_{args.tiles}^3_spans_R64",
+                       "spans": int(nspans), "resolution": RES, "power": POWER, "max_iters": MAX_ITERS,
+                       "bailout": BAILOUT, "math": "fast" if fast else "exact",
+                       "parallelism": f"spans sharded round-robin over {world} rank(s), meshes gathered to rank 0",
+                       "l2": "per-step working set (4.5 GB of sample grids streamed in 64 MiB groups + 0.7 GB of mesh) "
+                             "exceeds the 126 MB L2; no explicit flush"},
+            "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
+            "vertices": nv_tot, "indices": ni_tot,
+            "gpu_launches": int(launches2 - launches1),
+            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic instead of the fast mode")
+    ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_main(args)
+    return ours_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -64,6 +64,7 @@ EXPORTS = (
     "ctc_ctx_set_group_spans", "ctc_ctx_synchronize", "ctc_last_error", "ctc_kernel_launches",
     "ctc_de_batch", "ctc_de_batch_device", "ctc_sample_grids", "ctc_sample_grids_device",
     "ctc_mesh_spans", "ctc_mesh_spans_device", "ctc_mesh_result",
+    "ctc_iteration_stats", "ctc_fp32_peak_probe",
 )
 
 _lib = None
@@ -118,6 +119,10 @@ def lib() -> C.CDLL:
     L.ctc_mesh_spans_device.argtypes = [vp, shp, spn, sz, u32, vp, sz, vp, sz, vp, vp]
     L.ctc_mesh_result.restype = C.c_int
     L.ctc_mesh_result.argtypes = [vp, u64p, u64p, C.POINTER(CtcTimings)]
+    L.ctc_iteration_stats.restype = C.c_int
+    L.ctc_iteration_stats.argtypes = [vp, shp, spn, sz, u32, u64p]
+    L.ctc_fp32_peak_probe.restype = C.c_int
+    L.ctc_fp32_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _lib = L
     return L
 

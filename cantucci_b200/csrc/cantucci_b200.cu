@@ -566,4 +566,66 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
     return status;
 }
 
+int ctc_iteration_stats(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                        uint64_t out[3]) {
+    if (!ctx || !out) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh; uint32_t lg;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    rc = check_spans(ctx, spans, nspans, resolution, &lg); if (rc) return rc;
+    out[0] = out[1] = out[2] = 0;
+    if (nspans == 0) return CTC_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = upload_geom(ctx, spans, nspans, resolution); if (rc) return rc;
+    CK(ctx->pts_out.ensure(3 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->pts_out.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    const size_t n3 = (size_t)(resolution + 1) * (resolution + 1) * (resolution + 1);
+    const int variant = shape_variant(shape);
+    for (size_t s0 = 0; s0 < nspans; s0 += 32768) {
+        const uint32_t cnt = (uint32_t)((nspans - s0) < 32768 ? (nspans - s0) : 32768);
+        dim3 grid((unsigned)((n3 + kThreads - 1) / kThreads), cnt);
+        const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
+        unsigned long long* o = ctx->pts_out.as<unsigned long long>();
+        const float inv_r = 1.0f / (float)resolution;
+        if (variant == kVarP8) iteration_stats_kernel<kVarP8><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, resolution, lg, inv_r, o);
+        else if (variant == kVarGeneric) iteration_stats_kernel<kVarGeneric><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, resolution, lg, inv_r, o);
+        else iteration_stats_kernel<kVarSphere><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, resolution, lg, inv_r, o);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, ctx->pts_out.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    return CTC_OK;
+}
+
+int ctc_fp32_peak_probe(ctc_ctx* ctx, double* tflops, int* num_sms) {
+    if (!ctx || !tflops) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const unsigned blocks = (unsigned)ctx->num_sms * 8u;
+    const uint32_t iters = 4096;
+    CK(ctx->pts_out.ensure((size_t)blocks * kThreads * sizeof(float)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(a, ctx->stream));
+        fma_peak_kernel<<<blocks, kThreads, 0, ctx->stream>>>(ctx->pts_out.as<float>(), iters);
+        ctx->launches++;
+        CK(cudaEventRecord(b, ctx->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * kThreads;
+        if (rep >= 2 && ms > 0.f) { const double t = flops / (ms * 1e-3) / 1e12; if (t > best) best = t; }
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
+    if (num_sms) *num_sms = ctx->num_sms;
+    return CTC_OK;
+}
+
 }  // extern "C"

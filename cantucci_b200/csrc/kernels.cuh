@@ -532,6 +532,62 @@ quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __r
     }
 }
 
+// ---------------------------------------------------------------------------
+// Measurement aids (not on the hot path).
+// ---------------------------------------------------------------------------
+// Completed iterations and bail-outs over the sample lattices of a span batch (EXACT arithmetic,
+// i.e. the reference's own counts): out[0] += sum k, out[1] += #bailed, out[2] += #samples.
+// Feeds the algorithmic flop count flops(sample) = 75 k + 6 [bailed] + 10.
+template <int kVariant>
+__global__ void __launch_bounds__(kThreads)
+iteration_stats_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r,
+                       unsigned long long* __restrict__ out) {
+    const uint32_t n = R + 1u, n3 = n * n * n;
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    uint32_t k = 0, bailed = 0, cnt = 0;
+    if (i < n3) {
+        uint32_t x, y, z;
+        decode_sample(i, R, lg, x, y, z);
+        const SpanGeom g = geom[blockIdx.y];
+        const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
+        const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
+        const float pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));
+        if (kVariant != kVarSphere) {
+            (void)mandelbulb_de_exact<kVariant == kVarP8>(sh, px, py, pz, &k);
+            bailed = k < sh.max_iters;
+        }
+        cnt = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k += __shfl_xor_sync(0xffffffffu, k, o);
+        bailed += __shfl_xor_sync(0xffffffffu, bailed, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(&out[0], (unsigned long long)k);
+        atomicAdd(&out[1], (unsigned long long)bailed);
+        atomicAdd(&out[2], (unsigned long long)cnt);
+    }
+}
+
+// Dependent-free FFMA streams: the sustained FP32 FMA rate of this GPU at its running clock
+// (the denominator SURVEY.md 8d asks to be reported beside the nominal SMs*128*2*clock).
+__global__ void __launch_bounds__(kThreads)
+fma_peak_kernel(float* __restrict__ out, uint32_t iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * kThreads + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // Resets the call state at the start of a mesh call.
 __global__ void reset_state_kernel(MeshState* st) {
     st->total_v = 0; st->total_q = 0; st->group_base_v = 0; st->group_base_q = 0;

@@ -1,0 +1,150 @@
+"""Multi-GPU span scheduler: shard octree-leaf spans over ranks, gather meshes to rank 0.
+
+Replaces the reference's `ThreadPool::new(num_cpus)` + mpsc channel
+(/root/reference/src/mesh/mod.rs:60-62, 129-161): spans are independent (the
+one-cell skirt is recomputed, not exchanged; indices are span-local), so every
+rank meshes its own spans with the sm_100a kernels and the only exchange step is
+the variable-size gather of vertex / index bytes to rank 0 over NVLink (NCCL
+grouped send/recv -- NCCL has no gatherv).
+
+One process per GPU (torchrun); `torch.distributed` is plumbing only.  The same
+class runs on CPU tensors with the gloo backend when `mesher` is replaced by a
+stub, which is how the N>1 host logic is tested without GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_indices(nspans: int, world: int, rank: int) -> np.ndarray:
+    """Deal spans round-robin: neighbouring spans have similar cost (empty space vs surface),
+    so interleaving balances the ranks without a cost model."""
+    return np.arange(rank, nspans, world, dtype=np.int64)
+
+
+@dataclass
+class GatheredMeshes:
+    """Rank 0's view after the gather.  Vertices/indices are rank-major (rank 0's spans, then
+    rank 1's, ...); `span_v` / `span_i` give every span's [begin, end) in GLOBAL span order."""
+    vertices: object          # torch tensor [V, 7] f32 (28-byte Vertex records)
+    indices: object           # torch tensor [I] int32 (u32 bit patterns), span-local ids
+    span_v: np.ndarray        # int64 [nspans, 2]
+    span_i: np.ndarray        # int64 [nspans, 2]
+    n_vertices: int
+    n_indices: int
+
+
+class DeviceMesher:
+    """Runs ctc_mesh_spans_device on torch-owned device buffers of one rank."""
+
+    def __init__(self, ctx: _lib.Context, torch, device, vcap: int, icap: int, max_spans: int):
+        self.ctx, self.torch, self.device = ctx, torch, device
+        self.vcap, self.icap = int(vcap), int(icap)
+        self.v = torch.empty((self.vcap, 7), dtype=torch.float32, device=device)
+        self.i = torch.empty((self.icap,), dtype=torch.int32, device=device)
+        self.v_off = torch.zeros((max_spans + 1,), dtype=torch.int64, device=device)
+        self.i_off = torch.zeros((max_spans + 1,), dtype=torch.int64, device=device)
+
+    def launch(self, shape_struct, spans: np.ndarray, resolution: int, v=None, i=None, vcap=None, icap=None):
+        """Asynchronous: enqueue the whole mesh pipeline for `spans` on the context's stream."""
+        v = self.v if v is None else v
+        i = self.i if i is None else i
+        rc = _lib.lib().ctc_mesh_spans_device(
+            self.ctx.handle, C.byref(shape_struct), spans.ctypes.data, spans.shape[0], resolution,
+            v.data_ptr(), self.vcap if vcap is None else vcap, i.data_ptr(), self.icap if icap is None else icap,
+            self.v_off.data_ptr(), self.i_off.data_ptr())
+        self.ctx.check(rc)
+
+    def result(self, allow_lerp_assert: bool = False):
+        nv, ni = C.c_uint64(0), C.c_uint64(0)
+        t = _lib.CtcTimings()
+        rc = _lib.lib().ctc_mesh_result(self.ctx.handle, C.byref(nv), C.byref(ni), C.byref(t))
+        if rc == _lib.CTC_ERR_LERP_ASSERT and allow_lerp_assert:
+            rc = _lib.CTC_OK
+        self.ctx.check(rc)
+        return int(nv.value), int(ni.value), t
+
+
+class SpanScheduler:
+    """Shard -> mesh -> gather-to-rank-0 for one batch of spans."""
+
+    def __init__(self, dist, torch, rank: int, world: int, device, mesher, total_vcap: int = 0, total_icap: int = 0):
+        self.dist, self.torch, self.rank, self.world, self.device, self.mesher = dist, torch, rank, world, device, mesher
+        self.total_v = self.total_i = None
+        if rank == 0 and world > 1:
+            self.total_v = torch.empty((int(total_vcap), 7), dtype=torch.float32, device=device)
+            self.total_i = torch.empty((int(total_icap),), dtype=torch.int32, device=device)
+        self.counts = torch.zeros((2,), dtype=torch.int64, device=device)
+        self.all_counts = torch.zeros((world, 2), dtype=torch.int64, device=device)
+
+    def run(self, shape_struct, spans: np.ndarray, resolution: int) -> GatheredMeshes | None:
+        torch, dist, world, rank = self.torch, self.dist, self.world, self.rank
+        nspans = spans.shape[0]
+        mine = shard_indices(nspans, world, rank)
+        local = np.ascontiguousarray(spans[mine])
+        m = self.mesher
+        if world == 1:
+            m.launch(shape_struct, local, resolution)
+            nv, ni, _ = m.result()
+            off_v = m.v_off[: nspans + 1].cpu().numpy()
+            off_i = m.i_off[: nspans + 1].cpu().numpy()
+            return GatheredMeshes(m.v[:nv], m.i[:ni], np.stack([off_v[:-1], off_v[1:]], 1),
+                                  np.stack([off_i[:-1], off_i[1:]], 1), nv, ni)
+        # rank 0 meshes straight into the head of the gathered buffers
+        if rank == 0:
+            m.launch(shape_struct, local, resolution, v=self.total_v, i=self.total_i,
+                     vcap=self.total_v.shape[0], icap=self.total_i.shape[0])
+        else:
+            m.launch(shape_struct, local, resolution)
+        nv, ni, _ = m.result()
+        # exchange counts (2 x i64 per rank)
+        self.counts[0], self.counts[1] = nv, ni
+        dist.all_gather_into_tensor(self.all_counts.view(-1), self.counts)
+        counts = self.all_counts.cpu().numpy()
+        # variable-size gather: one grouped batch of NCCL send/recv
+        ops, tables = [], None
+        if rank == 0:
+            vb = np.concatenate([[0], np.cumsum(counts[:, 0])])
+            ib = np.concatenate([[0], np.cumsum(counts[:, 1])])
+            if vb[-1] > self.total_v.shape[0] or ib[-1] > self.total_i.shape[0]:
+                raise _lib.CantucciError(_lib.CTC_ERR_OVERFLOW, "gather buffers on rank 0 too small")
+            tables = [None] * world
+            for r in range(1, world):
+                n_r = len(shard_indices(nspans, world, r))
+                tables[r] = (torch.empty((n_r + 1,), dtype=torch.int64, device=self.device),
+                             torch.empty((n_r + 1,), dtype=torch.int64, device=self.device))
+                if counts[r, 0]:
+                    ops.append(dist.P2POp(dist.irecv, self.total_v[vb[r]:vb[r + 1]], r))
+                if counts[r, 1]:
+                    ops.append(dist.P2POp(dist.irecv, self.total_i[ib[r]:ib[r + 1]], r))
+                ops.append(dist.P2POp(dist.irecv, tables[r][0], r))
+                ops.append(dist.P2POp(dist.irecv, tables[r][1], r))
+        else:
+            n_r = len(mine)
+            if nv:
+                ops.append(dist.P2POp(dist.isend, m.v[:nv], 0))
+            if ni:
+                ops.append(dist.P2POp(dist.isend, m.i[:ni], 0))
+            ops.append(dist.P2POp(dist.isend, m.v_off[: n_r + 1], 0))
+            ops.append(dist.P2POp(dist.isend, m.i_off[: n_r + 1], 0))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rank != 0:
+            return None
+        span_v = np.zeros((nspans, 2), dtype=np.int64)
+        span_i = np.zeros((nspans, 2), dtype=np.int64)
+        for r in range(world):
+            idx = shard_indices(nspans, world, r)
+            if r == 0:
+                ov = m.v_off[: len(idx) + 1].cpu().numpy(); oi = m.i_off[: len(idx) + 1].cpu().numpy()
+            else:
+                ov = tables[r][0].cpu().numpy(); oi = tables[r][1].cpu().numpy()
+            span_v[idx, 0], span_v[idx, 1] = vb[r] + ov[:-1], vb[r] + ov[1:]
+            span_i[idx, 0], span_i[idx, 1] = ib[r] + oi[:-1], ib[r] + oi[1:]
+        return GatheredMeshes(self.total_v[: vb[-1]], self.total_i[: ib[-1]], span_v, span_i, int(vb[-1]), int(ib[-1]))

@@ -163,6 +163,18 @@ CTC_API int ctc_mesh_spans_device(ctc_ctx *ctx, const ctc_shape *shape, const ct
  * Returns CTC_OK, CTC_ERR_OVERFLOW or CTC_ERR_LERP_ASSERT. */
 CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indices, ctc_timings *timings);
 
+/* ---- measurement aids (not part of the reference's interface) ------------- */
+
+/* Iteration statistics of the sample lattices (exact arithmetic == the
+ * reference's counts): out[0] = sum of completed iterations, out[1] = samples
+ * that left through `r > bailout`, out[2] = samples.  Used for the algorithmic
+ * flop count flops(sample) = 75 k + 6 [bailed] + 10. Host pointers; synchronous. */
+CTC_API int ctc_iteration_stats(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                                uint32_t resolution, uint64_t out[3]);
+/* Sustained FP32 FMA rate of the device in TFLOP/s (FMA = 2 flops), measured
+ * with dependent-free FFMA streams on every SM. */
+CTC_API int ctc_fp32_peak_probe(ctc_ctx *ctx, double *tflops, int *num_sms);
+
 #ifdef __cplusplus
 }
 #endif

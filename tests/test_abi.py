@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def header_functions():
     src = open(os.path.join(ROOT, "include", "cantucci_b200.h")).read()
-    return sorted(set(re.findall(r"CTC_API[^;(]*?\b(ctc_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"CTC_API[^;(]*?\b(ctc_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_declares_the_expected_entry_points():
