@@ -139,7 +139,7 @@ def reference_main(args):
     if rank != 0:
         return 0
     spans = workload_spans()
-    sample = cpu_sample_spans(spans, 16)          # 256 of the 4096 spans per step
+    sample = cpu_sample_spans(spans, 4)           # 1024 of the 4096 spans per step
     times = []
     res = None
     for s in range(args.warmup + args.steps):
@@ -148,7 +148,7 @@ def reference_main(args):
             times.append(res["secs"])
     t = float(np.mean(times))
     value = res["samples"] / t
-    desc = f"{res['spans']} of {spans.shape[0]} spans per step (tiles with (ix+3iy+5iz)%16==0, spread evenly through the volume)"
+    desc = f"{res['spans']} of {spans.shape[0]} spans per step (tiles with (ix+3iy+5iz)%4==0, spread evenly through the volume)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -305,7 +305,7 @@ def ours_main(args):
         # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------
         cpu = None
         if world == 1 and not args.no_cpu:
-            sample = cpu_sample_spans(spans, 16 if args.tiles >= 16 else 4)
+            sample = cpu_sample_spans(spans, 4)
             r = run_cpu(sample)
             cpu = {"value": r["samples"] / r["secs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                    "sample": f"{r['spans']} of {nspans} spans (tiles with (ix+3iy+5iz)%stride==0), {r['secs']:.2f} s",

@@ -68,6 +68,14 @@ struct ctc_ctx {
     DevBuf pts_in, pts_out;
     PinnedBuf h_geom, h_state;
 
+    // pipelined device->host copies of the host-pointer mesh call
+    cudaStream_t copy_stream = nullptr;
+    unsigned long long* progress_h = nullptr;     // mapped pinned: totals after each group
+    unsigned long long* progress_d = nullptr;
+    size_t progress_cap = 0;                      // groups
+    std::vector<cudaEvent_t> group_events;
+    size_t n_groups = 0;
+
     // events of the last mesh call
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -162,8 +170,10 @@ GroupPlan plan_groups(const ctc_ctx* ctx, uint32_t R, uint32_t lg, size_t nspans
     p.chunks_per_span = p.words_per_span / p.chunk_words;
     size_t g = ctx->group_spans;
     if (g == 0) {
-        // keep a group's sample grids around 64 MiB so E1/E3 read them from L2 (126 MB)
-        g = (64ull << 20) / (p.n3 * 4);
+        // ~512 MiB of sample grids per launch group: large enough that the fixed cost of the small
+        // kernels (scan, prefix) and of the launches vanishes, small enough to pipeline the
+        // device->host copy of one group's mesh behind the next group's compute
+        g = (512ull << 20) / (p.n3 * 4);
         if (g < 1) g = 1;
     }
     const size_t max_by_cells = (size_t)1 << (31 - 3 * lg > 0 ? 31 - 3 * lg : 0);  // span<<lg3 | cell fits u32
@@ -205,7 +215,7 @@ void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint3
     const uint32_t core_blocks = lg >= 5 ? (uint32_t)(R3 / (8 * kThreads)) : 0u;
     const size_t rest = core_blocks ? n3 - R3 : n3;
     dim3 grid(core_blocks + (unsigned)((rest + kThreads - 1) / kThreads), nspans);
-    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, grids, stride,
+    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, 4.0f / (float)R, grids, stride,
                                                                              sign_bits, sign_stride, core_blocks);
     ctx->launches++;
 }
@@ -282,8 +292,19 @@ void launch_vertex(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, const
     ctx->launches++;
 }
 
+int ensure_progress(ctc_ctx* ctx, size_t groups) {
+    if (groups <= ctx->progress_cap) return CTC_OK;
+    if (ctx->progress_h) { cudaFreeHost(ctx->progress_h); ctx->progress_h = nullptr; ctx->progress_cap = 0; }
+    const size_t cap = groups + 64;
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->progress_h), cap * 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->progress_d), ctx->progress_h, 0));
+    ctx->progress_cap = cap;
+    return CTC_OK;
+}
+
 int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t R,
-                    ctc_vertex* d_v, size_t vcap, uint32_t* d_idx, size_t icap, uint64_t* d_v_off, uint64_t* d_i_off) {
+                    ctc_vertex* d_v, size_t vcap, uint32_t* d_idx, size_t icap, uint64_t* d_v_off, uint64_t* d_i_off,
+                    bool pipeline = false) {
     ShapeDev sh; uint32_t lg;
     int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
     rc = check_spans(ctx, spans, nspans, R, &lg); if (rc) return rc;
@@ -295,6 +316,7 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     CK(cudaStreamSynchronize(ctx->stream));   // staging buffers / events of a previous call
     ctx->ev_used = 0; ctx->ev_pairs.clear();
     ctx->mesh_pending = true;
+    ctx->n_groups = 0;
 
     CK(ctx->state.ensure(sizeof(MeshState)));
     MeshState* st = ctx->state.as<MeshState>();
@@ -327,8 +349,18 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     const int variant = shape_variant(shape);
     float* grids = ctx->grids.as<float>();
     const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
+    const size_t n_groups = (nspans + G - 1) / G;
+    if (pipeline) {
+        rc = ensure_progress(ctx, n_groups); if (rc) return rc;
+        while (ctx->group_events.size() < n_groups) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->group_events.push_back(e);
+        }
+    }
 
     for (size_t s0 = 0; s0 < nspans; s0 += G) {
+        const size_t gi = s0 / G;
         const uint32_t cnt = (uint32_t)((nspans - s0) < G ? (nspans - s0) : G);
         const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
         {   // pass 1
@@ -346,7 +378,8 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
             scan_chunks_kernel<<<1, kScanThreads, 0, ctx->stream>>>(
                 ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
                 (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
-                reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st);
+                reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st,
+                pipeline ? ctx->progress_d + 2 * gi : nullptr);
             apply_prefix_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->chunk_pre.as<uint2>(), gp.words_per_span,
                                                                     gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
                                                                     ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
@@ -359,12 +392,15 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         }
         {   // pass 3
             PassTimer t(ctx, 2);
-            quad_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
-                                                            grids, gp.n3, R, lg, gp.words_per_span, gp.chunk_words, st, d_idx,
-                                                            (unsigned long long)icap);
+            quad_kernel<<<vblocks, kThreads, 0, ctx->stream>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
+                                                              grids, gp.n3, R, lg, gp.words_per_span,
+                                                              ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
+                                                              (unsigned long long)icap);
             ctx->launches++;
         }
+        if (pipeline) CK(cudaEventRecord(ctx->group_events[gi], ctx->stream));
     }
+    ctx->n_groups = pipeline ? n_groups : 0;
     CK(cudaGetLastError());
     return CTC_OK;
 }
@@ -440,6 +476,9 @@ void ctc_ctx_destroy(ctc_ctx* c) {
         b->release();
     c->h_geom.release(); c->h_state.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
+    if (c->progress_h) cudaFreeHost(c->progress_h);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -551,18 +590,36 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
     CK(ctx->out_v.ensure((vcap ? vcap : 1) * sizeof(ctc_vertex)));
     CK(ctx->out_idx.ensure((icap ? icap : 1) * sizeof(uint32_t)));
     CK(ctx->off_v.ensure((nspans + 1) * 8)); CK(ctx->off_i.ensure((nspans + 1) * 8));
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int rc = mesh_spans_impl(ctx, shape, spans, nspans, resolution, ctx->out_v.as<ctc_vertex>(), vcap,
-                             ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>());
+                             ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
+                             /*pipeline=*/true);
     if (rc) return rc;
+    // Everything is enqueued.  Copy each group's slice of the mesh to the host on a second
+    // stream as soon as the group has finished, while the following groups are still computing.
+    size_t done_v = 0, done_i = 0;
+    for (size_t g = 0; g < ctx->n_groups; ++g) {
+        CK(cudaEventSynchronize(ctx->group_events[g]));
+        const unsigned long long tv = ctx->progress_h[2 * g], ti = 6ull * ctx->progress_h[2 * g + 1];
+        const size_t cv = tv < vcap ? (size_t)tv : vcap, ci = ti < icap ? (size_t)ti : icap;
+        if (cv > done_v) {
+            CK(cudaMemcpyAsync(v + done_v, ctx->out_v.as<ctc_vertex>() + done_v, (cv - done_v) * sizeof(ctc_vertex),
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+            done_v = cv;
+        }
+        if (ci > done_i) {
+            CK(cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+            done_i = ci;
+        }
+    }
     uint64_t nv = 0, ni = 0;
     const int status = mesh_result_impl(ctx, &nv, &ni, timings);
     if (status == CTC_ERR_CUDA) return status;
     CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    const size_t cv = nv < vcap ? (size_t)nv : vcap, ci = ni < icap ? (size_t)ni : icap;
-    if (cv) CK(cudaMemcpyAsync(v, ctx->out_v.p, cv * sizeof(ctc_vertex), cudaMemcpyDeviceToHost, ctx->stream));
-    if (ci) CK(cudaMemcpyAsync(idx, ctx->out_idx.p, ci * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     return status;
 }
 

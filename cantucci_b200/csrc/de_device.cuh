@@ -273,14 +273,16 @@ __device__ __noinline__ float mandelbulb_de_fast_on_axis(uint32_t P, uint32_t ma
     return canonical_x86_nan(0.5f * __logf(r) * r / dr);
 }
 
-template <bool kP8>
+// kCheckAxis = false: the caller guarantees (px, py) != (0, 0) (K1 tests it once per warp).
+template <bool kP8, bool kCheckAxis = true>
 __device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px, float py, float pz) {
     const uint32_t P = kP8 ? 8u : s.power;
-    if (px == 0.0f && py == 0.0f) return mandelbulb_de_fast_on_axis(P, s.max_iters, s.bailout, pz);
+    if (kCheckAxis && px == 0.0f && py == 0.0f) return mandelbulb_de_fast_on_axis(P, s.max_iters, s.bailout, pz);
     const float bail2 = s.bail2;
     float zx = px, zy = py, zz = pz;
-    float dr = 1.0f, r2 = 0.0f;
-    for (uint32_t it = 0; it < s.max_iters; ++it) {
+    float dr = 1.0f, r2;
+    uint32_t left = s.max_iters;                 // >= 1 (checked on the host, mandelbulb.rs:20)
+    do {
         const float z2 = zz * zz;
         const float w2 = fmaf(zx, zx, zy * zy);
         r2 = w2 + z2;
@@ -304,7 +306,7 @@ __device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px,
             cpow(zx * iw, zy * iw, P, cp, sp);      // cos(P phi), sin(P phi)
             zx = fmaf(st, cp, px); zy = fmaf(st, sp, py); zz = ct + pz;
         }
-    }
+    } while (--left);
     // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
     return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
 }
@@ -319,10 +321,10 @@ __device__ __forceinline__ float sphere_de(const ShapeDev& s, float px, float py
 // Shape dispatch.  kVariant: 0 = Mandelbulb P=8, 1 = Mandelbulb generic P, 2 = Sphere.
 enum : int { kVarP8 = 0, kVarGeneric = 1, kVarSphere = 2 };
 
-template <bool kFast, int kVariant>
+template <bool kFast, int kVariant, bool kCheckAxis = true>
 __device__ __forceinline__ float shape_de(const ShapeDev& s, float px, float py, float pz) {
     if (kVariant == kVarSphere) return sphere_de(s, px, py, pz);
-    if (kFast) return mandelbulb_de_fast<kVariant == kVarP8>(s, px, py, pz);
+    if (kFast) return mandelbulb_de_fast<kVariant == kVarP8, kCheckAxis>(s, px, py, pz);
     return mandelbulb_de_exact<kVariant == kVarP8>(s, px, py, pz);
 }
 

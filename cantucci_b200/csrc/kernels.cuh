@@ -109,7 +109,7 @@ __device__ __forceinline__ void decode_sample(uint32_t i, uint32_t R, uint32_t l
 // ---------------------------------------------------------------------------
 template <bool kFast, int kVariant>
 __global__ void __launch_bounds__(kThreads)
-sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r,
+sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r, float dvz4,
                     float* __restrict__ grids, size_t grid_stride,
                     uint32_t* __restrict__ sign_bits, uint32_t sign_stride /* words per span, 0 = no plane */,
                     uint32_t core_blocks) {
@@ -124,27 +124,31 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         const uint32_t yb = (wb >> (lg - 5)) & ((R >> 2) - 1u);
         const uint32_t xb = wb >> (2 * lg - 7);
         const uint32_t x = (xb << 1) | (lane >> 4), y = (yb << 2) | ((lane >> 2) & 3u);
-        uint32_t z = (zb << 5) | (lane & 3u);
+        const uint32_t z = (zb << 5) | (lane & 3u);
         // v = (x,y,z) as f32 / R  (exact: R is a power of two);  p = start + across * v  (buffer.rs:79-80)
         const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
         const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
-        float vz = __fmul_rn((float)z, inv_r);
-        const float dvz = 4.0f * inv_r;                 // exact increments: multiples of 1/R in [0,1]
+        float vz = __fmul_rn((float)z, inv_r);          // exact increments: multiples of 1/R in [0,1]
         float* out = grid + ((size_t)x * n + y) * n + z;                         // util/grid.rs:45-48
         uint32_t row_shift = (lane >> 2) << 2;          // this lane's row (xl,yl) nibble in a brick ballot
         asm volatile("" : "+r"(row_shift));             // keep it in a register (no S2R re-read per step)
         const float gs2 = g.s[2], ga2 = g.across[2];
         uint32_t word = 0;
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));
-            const float d = shape_de<kFast, kVariant>(sh, px, py, pz);
-            *out = d;
-            out += 4;
-            const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);
-            word = __funnelshift_r(word, b >> row_shift, 4);   // nibble j ends up at bits [4j, 4j+4)
-            vz = __fadd_rn(vz, dvz);
+        // the fast DE's on-axis special case is tested once per warp, not once per sample
+        const bool any_axis = kFast && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
+#define CTC_K1_STEPS(CHECK_AXIS)                                                                   \
+        _Pragma("unroll 1")                                                                        \
+        for (int j = 0; j < 8; ++j) {                                                              \
+            const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));                                   \
+            const float d = shape_de<kFast, kVariant, CHECK_AXIS>(sh, px, py, pz);                 \
+            *out = d;                                                                              \
+            out += 4;                                                                              \
+            const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);               \
+            word = __funnelshift_r(word, b >> row_shift, 4);   /* nibble j -> bits [4j, 4j+4) */   \
+            vz = __fadd_rn(vz, dvz4);                                                              \
         }
+        if (any_axis) { CTC_K1_STEPS(true) } else { CTC_K1_STEPS(false) }
+#undef CTC_K1_STEPS
         if (sign_stride != 0u && (lane & 3u) == 0u && word != 0u) {
             const uint32_t j0 = (x * n + y) * n + (zb << 5);
             const uint32_t sft = j0 & 31u;
@@ -311,7 +315,8 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ chunk_pre, uint32_t nchunks,
                    uint32_t chunks_per_span, uint32_t span0, uint32_t nspans_group,
                    unsigned long long* __restrict__ v_off, unsigned long long* __restrict__ i_off,
-                   unsigned long long vcap, unsigned long long icap, MeshState* __restrict__ st) {
+                   unsigned long long vcap, unsigned long long icap, MeshState* __restrict__ st,
+                   volatile unsigned long long* __restrict__ progress /* mapped pinned host memory or NULL */) {
     const unsigned long long base_v = st->total_v, base_q = st->total_q;
     uint32_t carry_v = 0, carry_q = 0;
     for (uint32_t t0 = 0; t0 < nchunks; t0 += kScanThreads) {
@@ -339,6 +344,8 @@ scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ c
         st->group_v = carry_v; st->group_q = carry_q;
         st->total_v = nv; st->total_q = nq;
         if (nv > vcap || 6ull * nq > icap) st->overflow = 1u;
+        // totals after this group, for the host's pipelined device->host copies
+        if (progress) { progress[0] = nv; progress[1] = nq; }
     }
 }
 
@@ -476,8 +483,7 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
 }
 
 // ---------------------------------------------------------------------------
-// E4: quads.  One thread per word of 32 lower corners (same grid as E1); the
-// ~85% of words without a sign-changing edge leave after three loads.
+// E4: quads.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t vertex_id(const uint32_t* __restrict__ active, const uint32_t* __restrict__ word_vpre,
                                               size_t span_w0, uint32_t c) {
@@ -493,39 +499,43 @@ __device__ __forceinline__ void store_quad(uint32_t* __restrict__ out_idx, unsig
     else      { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }   // [v0,v1,v2, v1,v3,v2]
 }
 
+// One thread per ACTIVE cell (the compacted list E2b wrote, cube(R) order): a lower corner can only
+// own a sign-changing edge if its cell is active, and there is about one quad per active cell, so
+// the list is a balanced, coalesced work list for the quads as well.  Persistent grid-stride loop
+// (the list length lives on the device).
 __global__ void __launch_bounds__(kThreads)
 quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __restrict__ word_qpre,
             const float* __restrict__ grids, size_t grid_stride,
-            uint32_t R, uint32_t lg, uint32_t words_per_span, uint32_t chunk_words,
+            uint32_t R, uint32_t lg, uint32_t words_per_span, const uint32_t* __restrict__ cell_of, uint32_t cell_cap,
             const MeshState* __restrict__ st, uint32_t* __restrict__ out_idx, unsigned long long icap) {
-    const uint32_t span = blockIdx.y, chunk = blockIdx.x;
-    if (threadIdx.x >= chunk_words) return;
-    const uint32_t word = chunk * chunk_words + threadIdx.x;
-    const size_t w0 = (size_t)span * words_per_span;
-    const size_t o = w0 + word;
-    const uint32_t bx = m.ex[o], by = m.ey[o], bz = m.ez[o];
-    uint32_t todo = bx | by | bz;
-    if (todo == 0u) return;
-    const uint32_t n = R + 1u, R2 = R << lg;
-    const float* __restrict__ g = grids + (size_t)span * grid_stride;
-    unsigned long long q = st->group_base_q + word_qpre[o];
-    while (todo) {
-        const uint32_t b = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        const uint32_t c = (word << 5) | b;
+    const uint32_t nv = min(st->group_v, cell_cap);
+    const unsigned long long base_q = st->group_base_q;
+    const uint32_t n = R + 1u, R2 = R << lg, lg3 = 3 * lg;
+    for (uint32_t v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
+        const uint32_t cell = cell_of[v];
+        const uint32_t span = cell >> lg3, c = cell & ((1u << lg3) - 1u);
+        const uint32_t b = c & 31u;
+        const size_t w0 = (size_t)span * words_per_span;
+        const size_t o = w0 + (c >> 5);
+        const uint32_t bx = m.ex[o], by = m.ey[o], bz = m.ez[o];
+        const uint32_t hx = (bx >> b) & 1u, hy = (by >> b) & 1u, hz = (bz >> b) & 1u;
+        if ((hx | hy | hz) == 0u) continue;
+        const uint32_t lt = (1u << b) - 1u;
+        // quads before this corner: whole words (prefix) + lower corners of this word, in corner order
+        unsigned long long q = base_q + word_qpre[o] + __popc(bx & lt) + __popc(by & lt) + __popc(bz & lt);
         const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
         // winding uses `dists[(x,y,z)] < 0.0`, not the sign bit (buffer.rs:310): -0.0 and NaN differ
-        const bool neg = g[((size_t)x * n + y) * n + z] < 0.0f;
-        const uint32_t v3 = vertex_id(m.active, word_vpre, w0, c);
-        if ((bx >> b) & 1u) {   // +x edge, buffer.rs:302-323
+        const bool neg = grids[(size_t)span * grid_stride + ((size_t)x * n + y) * n + z] < 0.0f;
+        const uint32_t v3 = word_vpre[o] + __popc(m.active[o] & lt);
+        if (hx) {   // +x edge, buffer.rs:302-323
             store_quad(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R - 1u),
                        vertex_id(m.active, word_vpre, w0, c - R), vertex_id(m.active, word_vpre, w0, c - 1u), v3);
         }
-        if ((by >> b) & 1u) {   // +y edge, buffer.rs:326-347 (winding flipped relative to x/z)
+        if (hy) {   // +y edge, buffer.rs:326-347 (winding flipped relative to x/z)
             store_quad(out_idx, q++, icap, !neg, vertex_id(m.active, word_vpre, w0, c - R2 - 1u),
                        vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - 1u), v3);
         }
-        if ((bz >> b) & 1u) {   // +z edge, buffer.rs:350-371
+        if (hz) {   // +z edge, buffer.rs:350-371
             store_quad(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R2 - R),
                        vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - R), v3);
         }
