@@ -61,18 +61,21 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The
+    sampler starts before the warm-up (nvidia-smi needs ~0.1 s to deliver its first row); rows are
+    time-stamped on arrival and only those inside [mark_begin, mark_end] are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,33 +84,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        # "under load": samples whose power draw is in the upper half of what was seen
-        if sm:
-            thr = 0.5 * (min(power) + max(power)) if power else 0
-            load = [s for s, p in zip(sm, power) if p >= thr] or sm
-            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                    "samples": len(sm), "power_w_max": max(power) if power else None}
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+        def parse(rows):
+            sm, smax, power, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+                    for k, nm in enumerate(names):
+                        if r[5 + k].lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    continue
+            return sm, smax, power, reasons
+
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30) + 0.03]
+        where = "inside the timed region"
+        if not inside:      # region shorter than one sampling period: take the rows right around it
+            inside = sorted(self.rows, key=lambda x: abs(x[0] - (self.t1 or 0)))[:3]
+            where = "nearest rows (timed region shorter than the 20 ms sampling period)"
+        sm, smax, power, reasons = parse(inside)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power), "where": where}
 
 
 # ---------------------------------------------------------------------------
@@ -217,14 +234,14 @@ def ours_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = ctx.kernel_launches()
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     launches1 = ctx.kernel_launches()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pass_ms = np.zeros(3)
     e0.record(stream)
@@ -232,6 +249,7 @@ def ours_main(args):
         step()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches2 = ctx.kernel_launches()
     # pass timings of the last step (CUDA events on the launching stream, inside the timed region)
@@ -335,7 +353,7 @@ def ours_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic instead of the fast mode")

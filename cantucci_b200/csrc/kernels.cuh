@@ -310,6 +310,7 @@ classify_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, ui
 // tables, capacity check, running totals.
 // ---------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 16;   // consecutive chunks per thread and pass
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ chunk_pre, uint32_t nchunks,
@@ -319,20 +320,30 @@ scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ c
                    volatile unsigned long long* __restrict__ progress /* mapped pinned host memory or NULL */) {
     const unsigned long long base_v = st->total_v, base_q = st->total_q;
     uint32_t carry_v = 0, carry_q = 0;
-    for (uint32_t t0 = 0; t0 < nchunks; t0 += kScanThreads) {
-        const uint32_t i = t0 + threadIdx.x;
-        uint2 c = make_uint2(0u, 0u);
-        if (i < nchunks) c = chunk_counts[i];
+    for (uint32_t t0 = 0; t0 < nchunks; t0 += kScanThreads * kScanItems) {
+        const uint32_t i0 = t0 + threadIdx.x * kScanItems;
+        uint2 c[kScanItems];
+        uint32_t sv = 0, sq = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            c[k] = (i0 + k < nchunks) ? chunk_counts[i0 + k] : make_uint2(0u, 0u);
+            sv += c[k].x; sq += c[k].y;
+        }
         uint32_t ev, eq, tv, tq;
-        block_exclusive_scan2<kScanThreads>(c.x, c.y, ev, eq, tv, tq);
-        if (i < nchunks) {
-            const uint32_t pv = carry_v + ev, pq = carry_q + eq;
-            chunk_pre[i] = make_uint2(pv, pq);
-            if (i % chunks_per_span == 0u) {
-                const uint32_t s = span0 + i / chunks_per_span;
-                v_off[s] = base_v + pv;
-                i_off[s] = 6ull * (base_q + pq);
+        block_exclusive_scan2<kScanThreads>(sv, sq, ev, eq, tv, tq);
+        uint32_t pv = carry_v + ev, pq = carry_q + eq;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const uint32_t i = i0 + k;
+            if (i < nchunks) {
+                chunk_pre[i] = make_uint2(pv, pq);
+                if (i % chunks_per_span == 0u) {
+                    const uint32_t s = span0 + i / chunks_per_span;
+                    v_off[s] = base_v + pv;
+                    i_off[s] = 6ull * (base_q + pq);
+                }
             }
+            pv += c[k].x; pq += c[k].y;
         }
         carry_v += tv; carry_q += tq;
     }

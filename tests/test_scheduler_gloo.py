@@ -1,0 +1,104 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU span scheduler's host logic: round-robin sharding,
+count exchange, variable-size gather to rank 0 and the global per-span offset tables.  The CUDA
+mesher is replaced by a deterministic stub with the same interface (DeviceMesher)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cantucci_b200.scheduler import SpanScheduler, shard_indices
+
+
+def span_mesh(row):
+    """Deterministic fake mesh of one span: sizes and contents derive from the span's coordinates."""
+    key = int(abs(float(row[0]) * 1000 + float(row[1]) * 100 + float(row[2]) * 10)) % 7
+    nv, nq = key * 3, key * 2          # key == 0 -> empty span
+    v = (np.arange(nv * 7, dtype=np.float32).reshape(nv, 7) + np.float32(row[0]))
+    i = (np.arange(nq * 6, dtype=np.int32) % max(nv, 1)).astype(np.int32)
+    return v, i
+
+
+class StubMesher:
+    def __init__(self, cap_v, cap_i, max_spans):
+        self.v = torch.zeros((cap_v, 7), dtype=torch.float32)
+        self.i = torch.zeros((cap_i,), dtype=torch.int32)
+        self.v_off = torch.zeros((max_spans + 1,), dtype=torch.int64)
+        self.i_off = torch.zeros((max_spans + 1,), dtype=torch.int64)
+        self._n = (0, 0)
+
+    def launch(self, shape_struct, spans, resolution, v=None, i=None, vcap=None, icap=None):
+        v = self.v if v is None else v
+        i = self.i if i is None else i
+        ov = oi = 0
+        for k, row in enumerate(spans):
+            mv, mi = span_mesh(row)
+            self.v_off[k], self.i_off[k] = ov, oi
+            v[ov:ov + len(mv)] = torch.from_numpy(mv)
+            i[oi:oi + len(mi)] = torch.from_numpy(mi)
+            ov += len(mv); oi += len(mi)
+        self.v_off[len(spans)], self.i_off[len(spans)] = ov, oi
+        self._n = (ov, oi)
+
+    def result(self):
+        return self._n[0], self._n[1], None
+
+
+def _worker(rank, world, port, spans, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesher = StubMesher(4096, 4096, len(spans))
+        sched = SpanScheduler(dist, torch, rank, world, torch.device("cpu"), mesher, 8192, 8192)
+        for _ in range(2):       # twice: buffers are reused between steps
+            got = sched.run(None, spans, 64)
+        if rank == 0:
+            torch.save({"v": got.vertices.clone(), "i": got.indices.clone(), "span_v": got.span_v,
+                        "span_i": got.span_i, "nv": got.n_vertices, "ni": got.n_indices}, out_path)
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,nspans", [(2, 13), (2, 2), (3, 10)])
+def test_gather_to_rank0_reassembles_every_span(tmp_path, world, nspans):
+    rng = np.random.default_rng(nspans)
+    spans = rng.uniform(-1, 1, size=(nspans, 6)).astype(np.float32)
+    out = str(tmp_path / "gathered.pt")
+    mp.spawn(_worker, args=(world, _free_port(), spans, out), nprocs=world, join=True)
+    got = torch.load(out, weights_only=False)
+    tot_v = tot_i = 0
+    for s in range(nspans):
+        v, i = span_mesh(spans[s])
+        a, b = got["span_v"][s]
+        c, d = got["span_i"][s]
+        assert b - a == len(v) and d - c == len(i)
+        assert np.array_equal(got["v"][a:b].numpy(), v)
+        assert np.array_equal(got["i"][c:d].numpy(), i)
+        tot_v += len(v); tot_i += len(i)
+    assert got["nv"] == tot_v and got["ni"] == tot_i
+    # rank-major layout: rank 0's spans first
+    first = shard_indices(nspans, world, 0)
+    assert got["span_v"][first[0]][0] == 0
+
+
+def test_round_robin_sharding_covers_every_span_once():
+    for world in (1, 2, 4, 8):
+        for n in (0, 1, 7, 64, 4096):
+            parts = [shard_indices(n, world, r) for r in range(world)]
+            allidx = np.sort(np.concatenate(parts)) if n else np.zeros(0, dtype=np.int64)
+            assert np.array_equal(allidx, np.arange(n))
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1
