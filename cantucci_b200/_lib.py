@@ -65,6 +65,7 @@ EXPORTS = (
     "ctc_de_batch", "ctc_de_batch_device", "ctc_sample_grids", "ctc_sample_grids_device",
     "ctc_mesh_spans", "ctc_mesh_spans_device", "ctc_mesh_result",
     "ctc_iteration_stats", "ctc_fp32_peak_probe",
+    "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
 )
 
 _lib = None
@@ -121,6 +122,16 @@ def lib() -> C.CDLL:
     L.ctc_mesh_result.argtypes = [vp, u64p, u64p, C.POINTER(CtcTimings)]
     L.ctc_iteration_stats.restype = C.c_int
     L.ctc_iteration_stats.argtypes = [vp, shp, spn, sz, u32, u64p]
+    L.ctc_device_alloc.restype = C.c_int
+    L.ctc_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.ctc_device_free.restype = C.c_int
+    L.ctc_device_free.argtypes = [vp, vp]
+    L.ctc_ipc_export.restype = C.c_int
+    L.ctc_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.ctc_ipc_open.restype = C.c_int
+    L.ctc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.ctc_ipc_close.restype = C.c_int
+    L.ctc_ipc_close.argtypes = [vp, vp]
     L.ctc_fp32_peak_probe.restype = C.c_int
     L.ctc_fp32_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _lib = L

@@ -175,6 +175,9 @@ GroupPlan plan_groups(const ctc_ctx* ctx, uint32_t R, uint32_t lg, size_t nspans
         // device->host copy of one group's mesh behind the next group's compute
         g = (512ull << 20) / (p.n3 * 4);
         if (g < 1) g = 1;
+        // ... and at least four groups per call (when there is enough work) so the copy pipeline has stages
+        const size_t quarter = (nspans + 3) / 4;
+        if (quarter >= 64 && g > quarter) g = quarter;
     }
     const size_t max_by_cells = (size_t)1 << (31 - 3 * lg > 0 ? 31 - 3 * lg : 0);  // span<<lg3 | cell fits u32
     if (g > max_by_cells) g = max_by_cells;
@@ -604,23 +607,68 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
         const size_t cv = tv < vcap ? (size_t)tv : vcap, ci = ti < icap ? (size_t)ti : icap;
         if (cv > done_v) {
             CK(cudaMemcpyAsync(v + done_v, ctx->out_v.as<ctc_vertex>() + done_v, (cv - done_v) * sizeof(ctc_vertex),
-                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+                               cudaMemcpyDefault, ctx->copy_stream));
             done_v = cv;
         }
         if (ci > done_i) {
             CK(cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
-                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+                               cudaMemcpyDefault, ctx->copy_stream));
             done_i = ci;
         }
     }
     uint64_t nv = 0, ni = 0;
     const int status = mesh_result_impl(ctx, &nv, &ni, timings);
     if (status == CTC_ERR_CUDA) return status;
-    CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     return status;
+}
+
+int ctc_device_alloc(ctc_ctx* ctx, size_t bytes, void** d_ptr) {
+    if (!ctx || !d_ptr) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return CTC_OK;
+}
+
+int ctc_device_free(ctc_ctx* ctx, void* d_ptr) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(d_ptr));
+    return CTC_OK;
+}
+
+int ctc_ipc_export(ctc_ctx* ctx, const void* d_ptr, unsigned char handle[64]) {
+    if (!ctx || !d_ptr || !handle) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle, &h, 64);
+    return CTC_OK;
+}
+
+int ctc_ipc_open(ctc_ctx* ctx, const unsigned char handle[64], void** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CTC_OK;
+}
+
+int ctc_ipc_close(ctc_ctx* ctx, void* d_ptr) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return CTC_OK;
 }
 
 int ctc_iteration_stats(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,

@@ -148,3 +148,103 @@ class SpanScheduler:
             span_v[idx, 0], span_v[idx, 1] = vb[r] + ov[:-1], vb[r] + ov[1:]
             span_i[idx, 0], span_i[idx, 1] = ib[r] + oi[:-1], ib[r] + oi[1:]
         return GatheredMeshes(self.total_v[: vb[-1]], self.total_i[: ib[-1]], span_v, span_i, int(vb[-1]), int(ib[-1]))
+
+
+# ---------------------------------------------------------------------------
+# Peer-memory gather: senders put their mesh slices straight into rank 0's buffers over NVLink
+# ---------------------------------------------------------------------------
+class _RawCuda:
+    """Minimal __cuda_array_interface__ wrapper so torch can view a raw device allocation."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerGatherScheduler:
+    """Shard -> mesh -> gather where the gather is one-sided: rank 0 owns the gathered vertex / index /
+    offset-table buffers (plain cudaMalloc, exported with CUDA IPC); every other rank maps them and
+    passes ITS region as the destination of ctc_mesh_spans, so each launch group's slice of the mesh is
+    copied over NVLink by the copy engines while the next group is computing.  No count exchange and no
+    receive has to be posted: regions have fixed capacities agreed at set-up, counts travel in the
+    offset tables.  One barrier per step tells rank 0 that every put has landed."""
+
+    def __init__(self, dist, torch, ctx: _lib.Context, rank: int, world: int, device, nspans: int,
+                 caps_v: list, caps_i: list):
+        self.dist, self.torch, self.ctx, self.rank, self.world, self.device = dist, torch, ctx, rank, world, device
+        self.nspans = nspans
+        self.n_r = [len(shard_indices(nspans, world, r)) for r in range(world)]
+        self.caps_v = [int(c) for c in caps_v]
+        self.caps_i = [int(c) for c in caps_i]
+        self.base_v = np.concatenate([[0], np.cumsum(self.caps_v)]).astype(np.int64)      # in vertices
+        self.base_i = np.concatenate([[0], np.cumsum(self.caps_i)]).astype(np.int64)      # in indices
+        self.base_t = np.concatenate([[0], np.cumsum([n + 1 for n in self.n_r])]).astype(np.int64)   # table entries
+        L = _lib.lib()
+        sizes = (int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, int(self.base_t[-1]) * 8, int(self.base_t[-1]) * 8)
+        self.ptrs = [C.c_void_p() for _ in sizes]
+        handles = [None]
+        if rank == 0:
+            hs = []
+            for p, nbytes in zip(self.ptrs, sizes):
+                ctx.check(L.ctc_device_alloc(ctx.handle, max(nbytes, 256), C.byref(p)))
+                h = C.create_string_buffer(64)
+                ctx.check(L.ctc_ipc_export(ctx.handle, p, h))
+                hs.append(h.raw)
+            handles = [hs]
+        if world > 1:
+            dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            for p, h in zip(self.ptrs, handles[0]):
+                ctx.check(L.ctc_ipc_open(ctx.handle, h, C.byref(p)))
+        self.sizes = sizes
+        # rank-local scratch for rank 0's own device call (offset tables live in the shared table buffers)
+        self._views = None
+        if rank == 0:
+            raw = [torch.as_tensor(_RawCuda(p.value, max(n, 256)), device=device) for p, n in zip(self.ptrs, sizes)]
+            self._views = (raw[0][: sizes[0]].view(torch.float32).view(-1, 7), raw[1][: sizes[1]].view(torch.int32),
+                           raw[2][: sizes[2]].view(torch.int64), raw[3][: sizes[3]].view(torch.int64))
+
+    def close(self):
+        L = _lib.lib()
+        for p in self.ptrs:
+            if p.value:
+                (L.ctc_device_free if self.rank == 0 else L.ctc_ipc_close)(self.ctx.handle, p)
+                p.value = None
+
+    def _region(self, r):
+        pv = self.ptrs[0].value + int(self.base_v[r]) * 28
+        pi = self.ptrs[1].value + int(self.base_i[r]) * 4
+        tv = self.ptrs[2].value + int(self.base_t[r]) * 8
+        ti = self.ptrs[3].value + int(self.base_t[r]) * 8
+        return pv, pi, tv, ti
+
+    def run(self, shape_struct, spans: np.ndarray, resolution: int) -> GatheredMeshes | None:
+        L, ctx, rank, world = _lib.lib(), self.ctx, self.rank, self.world
+        mine = shard_indices(self.nspans, world, rank)
+        local = np.ascontiguousarray(spans[mine])
+        pv, pi, tv, ti = self._region(rank)
+        if rank == 0:
+            ctx.check(L.ctc_mesh_spans_device(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0],
+                                              resolution, pv, self.caps_v[0], pi, self.caps_i[0], tv, ti))
+            rc = L.ctc_mesh_result(ctx.handle, None, None, None)
+        else:
+            rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
+                                  pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti, None)
+        ctx.check(rc)
+        if world > 1:
+            self.dist.barrier()          # every rank's puts have completed (each call synchronised its copy stream)
+        if rank != 0:
+            return None
+        v, i, tab_v, tab_i = self._views
+        tv_h, ti_h = tab_v.cpu().numpy(), tab_i.cpu().numpy()
+        span_v = np.zeros((self.nspans, 2), dtype=np.int64)
+        span_i = np.zeros((self.nspans, 2), dtype=np.int64)
+        nv = ni = 0
+        for r in range(world):
+            idx = shard_indices(self.nspans, world, r)
+            ov = tv_h[self.base_t[r]: self.base_t[r + 1]]
+            oi = ti_h[self.base_t[r]: self.base_t[r + 1]]
+            span_v[idx, 0], span_v[idx, 1] = self.base_v[r] + ov[:-1], self.base_v[r] + ov[1:]
+            span_i[idx, 0], span_i[idx, 1] = self.base_i[r] + oi[:-1], self.base_i[r] + oi[1:]
+            nv += int(ov[-1]); ni += int(oi[-1])
+        return GatheredMeshes(v, i, span_v, span_i, nv, ni)

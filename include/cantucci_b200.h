@@ -142,7 +142,10 @@ CTC_API int ctc_sample_grids_device(ctc_ctx *ctx, const ctc_shape *shape, const 
 /* Meshes every span.  Vertices of span s are v[v_off[s] .. v_off[s+1]) and
  * its indices idx[i_off[s] .. i_off[s+1]); indices are span-local (they
  * index into the span's own vertex range), ordered exactly as the reference
- * emits them.  v_off / i_off have nspans+1 entries.  Host pointers.
+ * emits them.  v_off / i_off have nspans+1 entries.  v, idx, v_off, i_off are
+ * HOST pointers (pinned memory copies fastest) or any other address the
+ * device can copy to (mapped peer-GPU memory, see ctc_ipc_open).  The copy of
+ * each launch group's slice overlaps the next group's compute.
  * timings may be NULL. */
 CTC_API int ctc_mesh_spans(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
                    uint32_t resolution,
@@ -162,6 +165,22 @@ CTC_API int ctc_mesh_spans_device(ctc_ctx *ctx, const ctc_shape *shape, const ct
  * total vertices / indices REQUIRED (even on overflow), pass timings.
  * Returns CTC_OK, CTC_ERR_OVERFLOW or CTC_ERR_LERP_ASSERT. */
 CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indices, ctc_timings *timings);
+
+/* ---- peer memory for the multi-GPU gather -------------------------------- */
+
+/* Plain cudaMalloc/cudaFree on the context's device (IPC handles need the base
+ * pointer of an allocation, which pooled allocators do not give). */
+CTC_API int ctc_device_alloc(ctc_ctx *ctx, size_t bytes, void **d_ptr);
+CTC_API int ctc_device_free(ctc_ctx *ctx, void *d_ptr);
+/* cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle: lets
+ * another process (one per GPU) map a buffer of this device.  `handle` is 64
+ * bytes.  The destination pointers of ctc_mesh_spans may be such mapped peer
+ * memory (or pinned host memory): each launch group's slice of the mesh is
+ * copied there as soon as the group finishes, overlapping the copy over NVLink
+ * with the next group's compute. */
+CTC_API int ctc_ipc_export(ctc_ctx *ctx, const void *d_ptr, unsigned char handle[64]);
+CTC_API int ctc_ipc_open(ctc_ctx *ctx, const unsigned char handle[64], void **d_ptr);
+CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
 
 /* ---- measurement aids (not part of the reference's interface) ------------- */
 
