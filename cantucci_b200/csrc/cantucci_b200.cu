@@ -408,11 +408,14 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     return CTC_OK;
 }
 
-int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc_timings* timings) {
+int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc_timings* timings,
+                     bool state_already_copied = false) {
     if (!ctx->mesh_pending) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "no mesh call pending");
     CK(cudaSetDevice(ctx->device));
-    CK(ctx->h_state.ensure(sizeof(MeshState)));
-    CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!state_already_copied) {
+        CK(ctx->h_state.ensure(sizeof(MeshState)));
+        CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     const MeshState* st = static_cast<const MeshState*>(ctx->h_state.p);
     if (n_vertices) *n_vertices = st->total_v;
@@ -598,8 +601,13 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
                              ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
                              /*pipeline=*/true);
     if (rc) return rc;
-    // Everything is enqueued.  Copy each group's slice of the mesh to the host on a second
-    // stream as soon as the group has finished, while the following groups are still computing.
+    // Everything is enqueued.  The offset tables follow the kernels on the compute stream; each
+    // group's slice of the mesh is copied on a second stream as soon as that group has finished,
+    // while the following groups are still computing.
+    CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    CK(ctx->h_state.ensure(sizeof(MeshState)));
+    CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
     size_t done_v = 0, done_i = 0;
     for (size_t g = 0; g < ctx->n_groups; ++g) {
         CK(cudaEventSynchronize(ctx->group_events[g]));
@@ -616,14 +624,9 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
             done_i = ci;
         }
     }
-    uint64_t nv = 0, ni = 0;
-    const int status = mesh_result_impl(ctx, &nv, &ni, timings);
-    if (status == CTC_ERR_CUDA) return status;
-    CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
-    return status;
+    uint64_t nv = 0, ni = 0;
+    return mesh_result_impl(ctx, &nv, &ni, timings, /*state_already_copied=*/true);
 }
 
 int ctc_device_alloc(ctc_ctx* ctx, size_t bytes, void** d_ptr) {

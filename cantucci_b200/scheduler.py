@@ -21,9 +21,13 @@ import numpy as np
 from . import _lib
 
 
-def shard_indices(nspans: int, world: int, rank: int) -> np.ndarray:
-    """Deal spans round-robin: neighbouring spans have similar cost (empty space vs surface),
-    so interleaving balances the ranks without a cost model."""
+def shard_indices(nspans: int, world: int, rank: int, mode: str = "interleave") -> np.ndarray:
+    """The spans rank `rank` meshes.  "interleave" deals them round-robin: neighbouring spans have
+    similar cost (empty space vs surface), so interleaving balances the ranks without a cost model.
+    "block" gives every rank one contiguous slice (used when the list is already N equal-cost parts)."""
+    if mode == "block":
+        per = (nspans + world - 1) // world
+        return np.arange(min(rank * per, nspans), min((rank + 1) * per, nspans), dtype=np.int64)
     return np.arange(rank, nspans, world, dtype=np.int64)
 
 
@@ -73,8 +77,10 @@ class DeviceMesher:
 class SpanScheduler:
     """Shard -> mesh -> gather-to-rank-0 for one batch of spans."""
 
-    def __init__(self, dist, torch, rank: int, world: int, device, mesher, total_vcap: int = 0, total_icap: int = 0):
+    def __init__(self, dist, torch, rank: int, world: int, device, mesher, total_vcap: int = 0, total_icap: int = 0,
+                 mode: str = "interleave"):
         self.dist, self.torch, self.rank, self.world, self.device, self.mesher = dist, torch, rank, world, device, mesher
+        self.mode = mode
         self.total_v = self.total_i = None
         if rank == 0 and world > 1:
             self.total_v = torch.empty((int(total_vcap), 7), dtype=torch.float32, device=device)
@@ -85,7 +91,7 @@ class SpanScheduler:
     def run(self, shape_struct, spans: np.ndarray, resolution: int) -> GatheredMeshes | None:
         torch, dist, world, rank = self.torch, self.dist, self.world, self.rank
         nspans = spans.shape[0]
-        mine = shard_indices(nspans, world, rank)
+        mine = shard_indices(nspans, world, rank, self.mode)
         local = np.ascontiguousarray(spans[mine])
         m = self.mesher
         if world == 1:
@@ -115,7 +121,7 @@ class SpanScheduler:
                 raise _lib.CantucciError(_lib.CTC_ERR_OVERFLOW, "gather buffers on rank 0 too small")
             tables = [None] * world
             for r in range(1, world):
-                n_r = len(shard_indices(nspans, world, r))
+                n_r = len(shard_indices(nspans, world, r, self.mode))
                 tables[r] = (torch.empty((n_r + 1,), dtype=torch.int64, device=self.device),
                              torch.empty((n_r + 1,), dtype=torch.int64, device=self.device))
                 if counts[r, 0]:
@@ -140,7 +146,7 @@ class SpanScheduler:
         span_v = np.zeros((nspans, 2), dtype=np.int64)
         span_i = np.zeros((nspans, 2), dtype=np.int64)
         for r in range(world):
-            idx = shard_indices(nspans, world, r)
+            idx = shard_indices(nspans, world, r, self.mode)
             if r == 0:
                 ov = m.v_off[: len(idx) + 1].cpu().numpy(); oi = m.i_off[: len(idx) + 1].cpu().numpy()
             else:
@@ -170,17 +176,19 @@ class PeerGatherScheduler:
     offset tables.  One barrier per step tells rank 0 that every put has landed."""
 
     def __init__(self, dist, torch, ctx: _lib.Context, rank: int, world: int, device, nspans: int,
-                 caps_v: list, caps_i: list):
+                 caps_v: list, caps_i: list, mode: str = "interleave"):
         self.dist, self.torch, self.ctx, self.rank, self.world, self.device = dist, torch, ctx, rank, world, device
-        self.nspans = nspans
-        self.n_r = [len(shard_indices(nspans, world, r)) for r in range(world)]
+        self.nspans, self.mode = nspans, mode
+        self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
+        self.n_r = [len(x) for x in self.shards]
         self.caps_v = [int(c) for c in caps_v]
         self.caps_i = [int(c) for c in caps_i]
         self.base_v = np.concatenate([[0], np.cumsum(self.caps_v)]).astype(np.int64)      # in vertices
         self.base_i = np.concatenate([[0], np.cumsum(self.caps_i)]).astype(np.int64)      # in indices
         self.base_t = np.concatenate([[0], np.cumsum([n + 1 for n in self.n_r])]).astype(np.int64)   # table entries
         L = _lib.lib()
-        sizes = (int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, int(self.base_t[-1]) * 8, int(self.base_t[-1]) * 8)
+        # one table buffer: all v_off tables, then all i_off tables (a single small D2H per step on rank 0)
+        sizes = (int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, 2 * int(self.base_t[-1]) * 8)
         self.ptrs = [C.c_void_p() for _ in sizes]
         handles = [None]
         if rank == 0:
@@ -202,7 +210,8 @@ class PeerGatherScheduler:
         if rank == 0:
             raw = [torch.as_tensor(_RawCuda(p.value, max(n, 256)), device=device) for p, n in zip(self.ptrs, sizes)]
             self._views = (raw[0][: sizes[0]].view(torch.float32).view(-1, 7), raw[1][: sizes[1]].view(torch.int32),
-                           raw[2][: sizes[2]].view(torch.int64), raw[3][: sizes[3]].view(torch.int64))
+                           raw[2][: sizes[2]].view(torch.int64))
+            self._local = np.ascontiguousarray(np.zeros((0, 6), dtype=np.float32))
 
     def close(self):
         L = _lib.lib()
@@ -215,13 +224,15 @@ class PeerGatherScheduler:
         pv = self.ptrs[0].value + int(self.base_v[r]) * 28
         pi = self.ptrs[1].value + int(self.base_i[r]) * 4
         tv = self.ptrs[2].value + int(self.base_t[r]) * 8
-        ti = self.ptrs[3].value + int(self.base_t[r]) * 8
+        ti = self.ptrs[2].value + (int(self.base_t[-1]) + int(self.base_t[r])) * 8
         return pv, pi, tv, ti
 
-    def run(self, shape_struct, spans: np.ndarray, resolution: int) -> GatheredMeshes | None:
+    def run(self, shape_struct, spans: np.ndarray, resolution: int, local: np.ndarray | None = None):
+        """One step.  `local` may carry this rank's pre-sliced spans.  Returns a LazyGather on rank 0
+        (device buffers are complete when this returns; the per-span tables are assembled on demand)."""
         L, ctx, rank, world = _lib.lib(), self.ctx, self.rank, self.world
-        mine = shard_indices(self.nspans, world, rank)
-        local = np.ascontiguousarray(spans[mine])
+        if local is None:
+            local = np.ascontiguousarray(spans[self.shards[rank]])
         pv, pi, tv, ti = self._region(rank)
         if rank == 0:
             ctx.check(L.ctc_mesh_spans_device(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0],
@@ -235,16 +246,37 @@ class PeerGatherScheduler:
             self.dist.barrier()          # every rank's puts have completed (each call synchronised its copy stream)
         if rank != 0:
             return None
-        v, i, tab_v, tab_i = self._views
-        tv_h, ti_h = tab_v.cpu().numpy(), tab_i.cpu().numpy()
-        span_v = np.zeros((self.nspans, 2), dtype=np.int64)
-        span_i = np.zeros((self.nspans, 2), dtype=np.int64)
-        nv = ni = 0
-        for r in range(world):
-            idx = shard_indices(self.nspans, world, r)
-            ov = tv_h[self.base_t[r]: self.base_t[r + 1]]
-            oi = ti_h[self.base_t[r]: self.base_t[r + 1]]
-            span_v[idx, 0], span_v[idx, 1] = self.base_v[r] + ov[:-1], self.base_v[r] + ov[1:]
-            span_i[idx, 0], span_i[idx, 1] = self.base_i[r] + oi[:-1], self.base_i[r] + oi[1:]
-            nv += int(ov[-1]); ni += int(oi[-1])
-        return GatheredMeshes(v, i, span_v, span_i, nv, ni)
+        tables = self._views[2].cpu().numpy()      # one small D2H: every rank's offset tables
+        return LazyGather(self, tables)
+
+
+class LazyGather:
+    """Rank 0's gathered result: device buffers + the raw offset tables; per-span [begin, end) ranges in
+    global span order are assembled on first use."""
+
+    def __init__(self, sched: "PeerGatherScheduler", tables: np.ndarray):
+        self._s, self._tables, self._built = sched, tables, None
+        self.vertices, self.indices = sched._views[0], sched._views[1]
+
+    def _build(self):
+        if self._built is None:
+            s = self._s
+            nt = int(s.base_t[-1])
+            tv_h, ti_h = self._tables[:nt], self._tables[nt:]
+            span_v = np.zeros((s.nspans, 2), dtype=np.int64)
+            span_i = np.zeros((s.nspans, 2), dtype=np.int64)
+            nv = ni = 0
+            for r in range(s.world):
+                idx = s.shards[r]
+                ov = tv_h[s.base_t[r]: s.base_t[r + 1]]
+                oi = ti_h[s.base_t[r]: s.base_t[r + 1]]
+                span_v[idx, 0], span_v[idx, 1] = s.base_v[r] + ov[:-1], s.base_v[r] + ov[1:]
+                span_i[idx, 0], span_i[idx, 1] = s.base_i[r] + oi[:-1], s.base_i[r] + oi[1:]
+                nv += int(ov[-1]); ni += int(oi[-1])
+            self._built = (span_v, span_i, nv, ni)
+        return self._built
+
+    span_v = property(lambda self: self._build()[0])
+    span_i = property(lambda self: self._build()[1])
+    n_vertices = property(lambda self: self._build()[2])
+    n_indices = property(lambda self: self._build()[3])

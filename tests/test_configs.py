@@ -1,0 +1,145 @@
+"""BASELINE.json configs 3, 4, 5 as parity / property tests (configs 1 and 2 live in test_gpu_parity.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cantucci_b200 as cb
+from cantucci_b200 import refine
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+class _OracleBulb(cb.Mandelbulb):
+    """TEST-ONLY: a Mandelbulb whose DE comes from the CPU oracle, to check the host-side refinement
+    logic without a GPU."""
+
+    def batch_min_distance_from(self, pts, ctx=None):
+        from oracle import oracle as O
+        return O.batch_min_distance_from(O.mandelbulb(self.power, self.max_iters, self.bailout),
+                                         np.asarray(pts, dtype=np.float32))
+
+
+# ------------------------------------------------------------------ config 3 (host logic, CPU) -----
+def test_config3_refinement_host_logic():
+    spans, cam = refine.config3_spans(_OracleBulb.classic(6, 2.5), 6)
+    # the camera sits on the -x tip of the bulb; the 25 focus rays all land in one leaf chain per level
+    assert abs(cam.position[0] + 1.105) < 2e-3 and cam.position[1] == 0 and cam.position[2] == 0
+    widths, counts = np.unique(np.round(spans[:, 3] - spans[:, 0], 5), return_counts=True)
+    assert len(spans) == 176
+    assert np.allclose(widths, [0.0375, 0.075, 0.15, 0.3, 0.6], atol=1e-5)      # depths 6..2
+    assert counts.tolist() == [32, 28, 28, 28, 60]
+    # leaves tile the bounding box exactly: volumes add up
+    vol = np.prod((spans[:, 3:] - spans[:, :3]).astype(np.float64), axis=1).sum()
+    assert abs(vol - 2.4 ** 3) < 1e-4
+
+
+# ------------------------------------------------------------------ config 3 (GPU parity) ----------
+@pytest.mark.gpu
+def test_config3_every_leaf_matches_oracle(oracle, ctx):
+    bulb = cb.Mandelbulb.classic(6, 2.5)
+    spans, _ = refine.config3_spans(bulb, 6, ctx)
+    ref_spans, _ = refine.config3_spans(_OracleBulb.classic(6, 2.5), 6)
+    assert np.array_equal(spans, ref_spans)                 # GPU DE drives the same refinement as the CPU DE
+    batch, t = cb.generate_for_boxes(spans, bulb, 64, ctx)
+    meshes, _ = oracle.generate_for_boxes_mt(oracle.mandelbulb(8, 6, 2.5), spans, 64)
+    counts = []
+    for k, (v, i, _) in enumerate(meshes):
+        got = batch.mesh(k)
+        assert np.array_equal(got.indices, i), k
+        assert np.array_equal(got.vertices.view(np.uint32), v.view(np.uint32)), k
+        counts.append(len(v))
+    # "wildly different vertex counts": empty leaves next to dense ones
+    assert min(counts) == 0 and max(counts) > 15000
+    fast, _ = cb.generate_for_boxes(spans, cb.Mandelbulb.classic(6, 2.5, fast=True), 64, ctx)
+    assert abs(len(fast.vertices) - len(batch.vertices)) <= len(batch.vertices) // 2000 + 8
+
+
+# ------------------------------------------------------------------ config 4 (power sweep) ---------
+def _tiles16():
+    return cb.tile_volume(cb.Span((-1.2, -1.2, -1.2), (1.2, 1.2, 1.2)), 16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("power", [2, 4, 8, 16])
+@pytest.mark.parametrize("max_iters", [32, 128])
+def test_config4_power_sweep_subset_against_oracle(oracle, ctx, power, max_iters):
+    """Eight tiles of the 1024^3 volume per (P, max_iters): grids against the oracle (bit-exact for
+    P=8, tolerance otherwise), topology wherever the sign field agrees."""
+    tiles = _tiles16()
+    pick = tiles[np.random.default_rng(power * 1000 + max_iters).choice(len(tiles), 8, replace=False)]
+    pick[0] = tiles[(8 * 16 + 8) * 16 + 3]      # one tile that certainly cuts the surface
+    sh = oracle.mandelbulb(power, max_iters, 2.5)
+    exact = cb.Mandelbulb(power, max_iters, 2.5)
+    g_exact = cb.sample_grids(pick, exact, 64, ctx)
+    g_fast = cb.sample_grids(pick, cb.Mandelbulb(power, max_iters, 2.5, fast=True), 64, ctx)
+    flips_exact = flips_fast = total = 0
+    for k, row in enumerate(pick):
+        want = oracle.sample_grid(sh, oracle.make_span(row[:3], row[3:]), 64)
+        if power == 8:
+            assert np.array_equal(bits(g_exact[k]), bits(want)), k
+        flips_exact += int(np.sum((bits(g_exact[k]) >> 31) != (bits(want) >> 31)))
+        flips_fast += int(np.sum((bits(g_fast[k]) >> 31) != (bits(want) >> 31)))
+        total += want.size
+        # far-field samples (escape at once) agree tightly in every mode
+        far = want > 0.5
+        if far.any():
+            assert np.max(np.abs(g_fast[k][far] - want[far]) / want[far]) < 1e-5
+            assert np.max(np.abs(g_exact[k][far] - want[far]) / want[far]) < 1e-5
+    # chaotic interior: signs of a few samples near the escape boundary may flip
+    assert flips_exact / total < (0 if power == 8 else 2e-3) + 1e-12
+    assert flips_fast / total < 2e-3
+    if power == 8:
+        batch, _ = cb.generate_for_boxes(pick, exact, 64, ctx)
+        meshes, _ = oracle.generate_for_boxes_mt(sh, pick, 64)
+        for k, m in enumerate(meshes):
+            if m is None:        # the reference panicked (lerp assert) -- cannot happen with status OK
+                continue
+            assert np.array_equal(batch.mesh(k).indices, m[1]) and np.array_equal(batch.mesh(k).vertices.view(np.uint32), m[0].view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("power,max_iters", [(8, 32), (8, 128), (2, 32), (16, 128)])
+def test_config4_full_1024_volume_properties(ctx, power, max_iters):
+    """The whole 1024^3 volume (4096 spans) in fast mode: size-independent properties."""
+    import torch
+    from cantucci_b200 import _lib
+    from cantucci_b200.scheduler import DeviceMesher
+    tiles = _tiles16()
+    sh = cb.Mandelbulb(power, max_iters, 2.5, fast=True)._ctc_shape()
+    dev = torch.device("cuda", 0)
+    m = DeviceMesher(ctx, torch, dev, 40_000_000, 240_000_000, len(tiles))
+    runs = []
+    for _ in range(2):
+        m.launch(sh, tiles, 64)
+        nv, ni, t = m.result(allow_lerp_assert=True)
+        assert 0 < nv <= m.vcap and ni % 6 == 0 and ni <= m.icap
+        v_off = m.v_off[: len(tiles) + 1].cpu().numpy(); i_off = m.i_off[: len(tiles) + 1].cpu().numpy()
+        assert v_off[-1] == nv and i_off[-1] == ni and np.all(np.diff(v_off) >= 0) and np.all(np.diff(i_off) >= 0)
+        runs.append((nv, ni, int(m.i[:ni].to(torch.int64).sum()), float(m.v[:nv, :3].abs().max())))
+    assert runs[0] == runs[1]                                   # idempotent, deterministic
+    assert runs[0][3] <= 1.2 + 2 * 0.15 / 64 + 1e-6             # vertices inside the skirted volume
+    # span-local indices stay inside their span's vertex range
+    cnt_v = torch.from_numpy(np.diff(v_off)).to(dev)
+    span_of_index = torch.repeat_interleave(torch.arange(len(tiles), device=dev), torch.from_numpy(np.diff(i_off)).to(dev))
+    assert bool((m.i[:ni].to(torch.int64) < cnt_v[span_of_index]).all())
+
+
+# ------------------------------------------------------------------ config 5 (4096^3 as 64^3 spans) -
+@pytest.mark.gpu
+def test_config5_4096_volume_sharded_subset_and_oracle_sample(oracle, ctx):
+    """Config 5 is 262 144 spans; the full volume is exercised by `bench.py --tiles 64`.  Here: a
+    4096-span slab of it through the device API, plus 24 of its spans against the oracle."""
+    tiles = cb.tile_volume(cb.Span((-1.2, -1.2, -1.2), (1.2, 1.2, 1.2)), 64)
+    assert tiles.shape == (262144, 6)
+    slab = np.ascontiguousarray(tiles[31 * 4096: 32 * 4096])            # the x-slab through the middle
+    bulb = cb.Mandelbulb.classic(6, 2.5)
+    batch, t = cb.generate_for_boxes(slab, bulb, 64, ctx)
+    assert t.vertices == len(batch.vertices) > 1_000_000
+    pick = np.random.default_rng(5).choice(len(slab), 24, replace=False)
+    meshes, _ = oracle.generate_for_boxes_mt(oracle.mandelbulb(8, 6, 2.5), slab[pick], 64)
+    for k, (v, i, _) in zip(pick, meshes):
+        got = batch.mesh(int(k))
+        assert np.array_equal(got.indices, i) and np.array_equal(got.vertices.view(np.uint32), v.view(np.uint32))
