@@ -66,7 +66,7 @@ struct ctc_ctx {
     DevBuf geom, grids, sign_bits, m_active, m_ex, m_ey, m_ez, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
     DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
     DevBuf pts_in, pts_out;
-    PinnedBuf h_geom, h_state;
+    PinnedBuf h_geom, h_state, h_tables;
 
     // pipelined device->host copies of the host-pointer mesh call
     cudaStream_t copy_stream = nullptr;
@@ -213,10 +213,11 @@ struct PassTimer {
 template <bool kFast, int kVariant>
 void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint32_t R, uint32_t lg, float* grids,
                    size_t stride, uint32_t nspans, size_t n3, uint32_t* sign_bits, uint32_t sign_stride) {
-    // R >= 32: the R^3 core goes to the warp-per-2x4x32-block path (2048 samples per CTA)
-    const size_t R3 = (size_t)R * R * R;
-    const uint32_t core_blocks = lg >= 5 ? (uint32_t)(R3 / (8 * kThreads)) : 0u;
-    const size_t rest = core_blocks ? n3 - R3 : n3;
+    // R >= 32: the R^3 core and the x = R / y = R faces go to the warp-per-256-sample-block path
+    const size_t R2 = (size_t)R * R, R3 = R2 * R;
+    const size_t warp_blocks = lg >= 5 ? (R3 + 2 * R2) / 256 : 0;
+    const uint32_t core_blocks = (uint32_t)((warp_blocks + 7) / 8);
+    const size_t rest = core_blocks ? R2 + 3 * (size_t)R + 1 : n3;
     dim3 grid(core_blocks + (unsigned)((rest + kThreads - 1) / kThreads), nspans);
     sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, 4.0f / (float)R, grids, stride,
                                                                              sign_bits, sign_stride, core_blocks);
@@ -480,7 +481,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
                       &c->chunk_pre, &c->word_vpre, &c->word_qpre, &c->cell_of, &c->state, &c->out_v, &c->out_idx,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out})
         b->release();
-    c->h_geom.release(); c->h_state.release();
+    c->h_geom.release(); c->h_state.release(); c->h_tables.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
     if (c->progress_h) cudaFreeHost(c->progress_h);
@@ -601,11 +602,24 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
                              ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
                              /*pipeline=*/true);
     if (rc) return rc;
-    // Everything is enqueued.  The offset tables follow the kernels on the compute stream; each
-    // group's slice of the mesh is copied on a second stream as soon as that group has finished,
-    // while the following groups are still computing.
-    CK(cudaMemcpyAsync(v_off, ctx->off_v.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(i_off, ctx->off_i.p, (nspans + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    // Everything is enqueued.  The offset tables follow the kernels on the compute stream (straight
+    // to the destination when it is device/peer memory, through a pinned staging buffer when it is
+    // host memory, so the call never blocks on a pageable copy); each group's slice of the mesh is
+    // copied on a second stream as soon as that group has finished, while the following groups are
+    // still computing.
+    cudaPointerAttributes pa{};
+    const bool tables_on_device = cudaPointerGetAttributes(&pa, v_off) == cudaSuccess &&
+                                  (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    (void)cudaGetLastError();
+    const size_t tbytes = (nspans + 1) * 8;
+    if (tables_on_device) {
+        CK(cudaMemcpyAsync(v_off, ctx->off_v.p, tbytes, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(i_off, ctx->off_i.p, tbytes, cudaMemcpyDefault, ctx->stream));
+    } else {
+        CK(ctx->h_tables.ensure(2 * tbytes));
+        CK(cudaMemcpyAsync(ctx->h_tables.p, ctx->off_v.p, tbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(static_cast<char*>(ctx->h_tables.p) + tbytes, ctx->off_i.p, tbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(ctx->h_state.ensure(sizeof(MeshState)));
     CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
     size_t done_v = 0, done_i = 0;
@@ -626,7 +640,12 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
     }
     CK(cudaStreamSynchronize(ctx->copy_stream));
     uint64_t nv = 0, ni = 0;
-    return mesh_result_impl(ctx, &nv, &ni, timings, /*state_already_copied=*/true);
+    const int status = mesh_result_impl(ctx, &nv, &ni, timings, /*state_already_copied=*/true);   // syncs the compute stream
+    if (status != CTC_ERR_CUDA && !tables_on_device) {
+        memcpy(v_off, ctx->h_tables.p, tbytes);
+        memcpy(i_off, static_cast<char*>(ctx->h_tables.p) + tbytes, tbytes);
+    }
+    return status;
 }
 
 int ctc_device_alloc(ctc_ctx* ctx, size_t bytes, void** d_ptr) {

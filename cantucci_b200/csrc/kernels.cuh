@@ -99,13 +99,13 @@ __device__ __forceinline__ void decode_sample(uint32_t i, uint32_t R, uint32_t l
 // extraction passes never re-read the 4-byte samples except at active cells.
 // The plane must be zeroed before the launch.
 //
-// Blocks [0, core_blocks): the R^3 core for R >= 32.  A warp owns a 2x4x32 block
-// of samples and walks it in 8 steps of one 2x4x4 brick (lane = xl:yl:zl), so
-// iteration counts inside a warp stay coherent, the per-warp set-up (decode,
-// geometry load, x/y position) is paid once per 256 samples, and the 8 ballots
-// assemble the 8 row words of the block's sign bits without shared memory.
-// Remaining blocks: faces / edges / corner (and everything when R < 32), one
-// thread per sample.
+// Blocks [0, core_blocks), R >= 32: a warp owns a 2x4x32 block of the R^3 core
+// (or a 1x8x32 / 8x1x32 block of the x = R / y = R face) and walks it in 8 steps
+// of one 32-sample brick, so iteration counts inside a warp stay coherent, the
+// per-warp set-up (decode, geometry load, x/y position) is paid once per 256
+// samples, and the 8 ballots assemble the 8 row words of the block's sign bits
+// without shared memory.  Remaining blocks: the z = R face, edges and corner
+// (and everything when R < 32), one thread per sample.
 // ---------------------------------------------------------------------------
 template <bool kFast, int kVariant>
 __global__ void __launch_bounds__(kThreads)
@@ -118,12 +118,23 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
     float* __restrict__ grid = grids + (size_t)blockIdx.y * grid_stride;
     uint32_t* __restrict__ plane = sign_bits + (size_t)blockIdx.y * sign_stride;
     if (blockIdx.x < core_blocks) {
+        // warp-blocks: [0, R^3/256) core 2x4x32; then R^2/256 blocks 1x8x32 of the x = R face; then
+        // R^2/256 blocks 8x1x32 of the y = R face.  All three walk 32 z-samples in 8 brick steps.
         const uint32_t lane = threadIdx.x & 31u;
-        const uint32_t wb = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);   // 2x4x32 block id, z fastest
-        const uint32_t zb = wb & ((R >> 5) - 1u);
-        const uint32_t yb = (wb >> (lg - 5)) & ((R >> 2) - 1u);
-        const uint32_t xb = wb >> (2 * lg - 7);
-        const uint32_t x = (xb << 1) | (lane >> 4), y = (yb << 2) | ((lane >> 2) & 3u);
+        const uint32_t wb = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+        const uint32_t n_core = 1u << (3 * lg - 8), n_face = 1u << (2 * lg - 8);
+        if (wb >= n_core + 2u * n_face) return;
+        uint32_t x, y, zb;
+        if (wb < n_core) {
+            zb = wb & ((R >> 5) - 1u);
+            x = ((wb >> (2 * lg - 7)) << 1) | (lane >> 4);
+            y = (((wb >> (lg - 5)) & ((R >> 2) - 1u)) << 2) | ((lane >> 2) & 3u);
+        } else {
+            const uint32_t f = wb - n_core, ff = f & (n_face - 1u);
+            zb = ff & ((R >> 5) - 1u);
+            const uint32_t t = ((ff >> (lg - 5)) << 3) | (lane >> 2);
+            if (f < n_face) { x = R; y = t; } else { x = t; y = R; }
+        }
         const uint32_t z = (zb << 5) | (lane & 3u);
         // v = (x,y,z) as f32 / R  (exact: R is a power of two);  p = start + across * v  (buffer.rs:79-80)
         const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
@@ -157,12 +168,25 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         }
         return;
     }
-    const uint32_t n3 = n * n * n;
-    const uint32_t R3 = R << (2 * lg);
-    const uint32_t i = (blockIdx.x - core_blocks) * kThreads + threadIdx.x + (core_blocks ? R3 : 0u);
-    if (i >= n3) return;
+    // one thread per remaining sample: everything when R < 32, else the z = R face, the three edges
+    // x=y=R / x=z=R / y=z=R and the corner (R^2 + 3R + 1 samples)
+    const uint32_t i = (blockIdx.x - core_blocks) * kThreads + threadIdx.x;
     uint32_t x, y, z;
-    decode_sample(i, R, lg, x, y, z);
+    if (core_blocks == 0u) {
+        if (i >= n * n * n) return;
+        decode_sample(i, R, lg, x, y, z);
+    } else {
+        const uint32_t R2 = R << lg;
+        if (i < R2) { x = i >> lg; y = i & (R - 1u); z = R; }
+        else {
+            const uint32_t e = (i - R2) >> lg, t = (i - R2) & (R - 1u);
+            if (e == 0u)      { x = R; y = R; z = t; }
+            else if (e == 1u) { x = R; y = t; z = R; }
+            else if (e == 2u) { x = t; y = R; z = R; }
+            else if (e == 3u && t == 0u) { x = R; y = R; z = R; }
+            else return;
+        }
+    }
     const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
     const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
     const float pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));

@@ -77,18 +77,21 @@ def test_config4_power_sweep_subset_against_oracle(oracle, ctx, power, max_iters
     g_fast = cb.sample_grids(pick, cb.Mandelbulb(power, max_iters, 2.5, fast=True), 64, ctx)
     flips_exact = flips_fast = total = 0
     for k, row in enumerate(pick):
-        want = oracle.sample_grid(sh, oracle.make_span(row[:3], row[3:]), 64)
+        want, iters = oracle.sample_grid_iters(sh, oracle.make_span(row[:3], row[3:]), 64)
         if power == 8:
             assert np.array_equal(bits(g_exact[k]), bits(want)), k
-        flips_exact += int(np.sum((bits(g_exact[k]) >> 31) != (bits(want) >> 31)))
-        flips_fast += int(np.sum((bits(g_fast[k]) >> 31) != (bits(want) >> 31)))
-        total += want.size
+        # Escaping samples only: after 32..128 iterations the sign of an interior sample is the sign of
+        # ln(r) on a chaotic orbit, which two libm implementations cannot agree on (P != 8).
+        esc = iters < max_iters
+        flips_exact += int(np.sum(((bits(g_exact[k]) >> 31) != (bits(want) >> 31)) & esc))
+        flips_fast += int(np.sum(((bits(g_fast[k]) >> 31) != (bits(want) >> 31)) & esc))
+        total += int(esc.sum())
         # far-field samples (escape at once) agree tightly in every mode
         far = want > 0.5
         if far.any():
             assert np.max(np.abs(g_fast[k][far] - want[far]) / want[far]) < 1e-5
             assert np.max(np.abs(g_exact[k][far] - want[far]) / want[far]) < 1e-5
-    # chaotic interior: signs of a few samples near the escape boundary may flip
+    # samples whose escape iteration sits on the bailout boundary may still flip
     assert flips_exact / total < (0 if power == 8 else 2e-3) + 1e-12
     assert flips_fast / total < 2e-3
     if power == 8:
