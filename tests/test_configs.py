@@ -80,9 +80,10 @@ def test_config4_power_sweep_subset_against_oracle(oracle, ctx, power, max_iters
         want, iters = oracle.sample_grid_iters(sh, oracle.make_span(row[:3], row[3:]), 64)
         if power == 8:
             assert np.array_equal(bits(g_exact[k]), bits(want)), k
-        # Escaping samples only: after 32..128 iterations the sign of an interior sample is the sign of
-        # ln(r) on a chaotic orbit, which two libm implementations cannot agree on (P != 8).
-        esc = iters < max_iters
+        # Samples that escape within 6 iterations only: later escapes and interior samples sit on
+        # chaotic orbits (a 1-ulp libm difference grows by ~P per iteration), so neither their escape
+        # time nor the sign of ln(r) after 32..128 iterations can agree between two libm's (P != 8).
+        esc = iters <= 6
         flips_exact += int(np.sum(((bits(g_exact[k]) >> 31) != (bits(want) >> 31)) & esc))
         flips_fast += int(np.sum(((bits(g_fast[k]) >> 31) != (bits(want) >> 31)) & esc))
         total += int(esc.sum())
@@ -137,7 +138,7 @@ def test_config5_4096_volume_sharded_subset_and_oracle_sample(oracle, ctx):
     4096-span slab of it through the device API, plus 24 of its spans against the oracle."""
     tiles = cb.tile_volume(cb.Span((-1.2, -1.2, -1.2), (1.2, 1.2, 1.2)), 64)
     assert tiles.shape == (262144, 6)
-    slab = np.ascontiguousarray(tiles[31 * 4096: 32 * 4096])            # the x-slab through the middle
+    slab = np.ascontiguousarray(tiles[10 * 4096: 11 * 4096])            # an x-slab cutting the bulb, clear of the axis planes
     bulb = cb.Mandelbulb.classic(6, 2.5)
     batch, t = cb.generate_for_boxes(slab, bulb, 64, ctx)
     assert t.vertices == len(batch.vertices) > 1_000_000
