@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcantucci_b200.so")
+# CANTUCCI_B200_LIB selects another build of the same library (A/B kernel experiments)
+LIB_PATH = os.environ.get("CANTUCCI_B200_LIB") or os.path.join(_HERE, "libcantucci_b200.so")
 
 CTC_OK = 0
 CTC_ERR_INVALID_ARGUMENT = 1

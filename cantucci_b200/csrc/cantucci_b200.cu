@@ -384,7 +384,7 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
                 (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
                 reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st,
                 pipeline ? ctx->progress_d + 2 * gi : nullptr);
-            apply_prefix_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->chunk_pre.as<uint2>(), gp.words_per_span,
+            apply_prefix_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), gp.words_per_span,
                                                                     gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
                                                                     ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
                                                                     cell_cap);

@@ -220,38 +220,48 @@ __device__ __forceinline__ void cpow(float a, float b, uint32_t n, float& re, fl
     re = rr; im = ri;
 }
 
-// One power-8 step of the FAST path.  Same map as rotate_inner_p8_scalar, but
-//  * the azimuth polynomial is evaluated on the unit vector (u,v) = (x,y)/w, so there is no
-//    division by w^8 (which underflows near the z axis and would inject inf/NaN):
-//        X = A c8,  Y = A s8,  A = z8 - 28 z6 w2 + 70 z4 w4 - 28 z2 w6 + w8,
-//        c8 = u8 - 28 u6 v2 + 70 u4 v4 - 28 u2 v6 - v8   [sic: -v8, as the reference's -y8]
-//        s8 = 8 u v (u6 - 7 u4 v2 + 7 u2 v4 - v6)
-//  * the quartics in (a,b) = (u2,v2) / (z2,w2) are factored:
-//        a4 - 28 a3 b + 70 a2 b2 - 28 a b3 - b4 = S (D - 28 m) + 70 m^2
-//        a4 - 28 a3 b + 70 a2 b2 - 28 a b3 + b4 = S (S - 28 m) + 68 m^2
-//        a3 - 7 a2 b + 7 a b2 - b3            = (a - b)(S - 6 m)
-//    with S = a2 + b2, D = a2 - b2, m = a b.
-// ~46 FMA-pipe instructions + 2 MUFU per iteration against 75 algorithmic flops.
-// w2 is clamped away from zero before the rsqrt, so the step is finite for every finite input.
+// One power-8 step of the FAST path.  Same map as rotate_inner_p8_scalar:
+//     X = a (x8 - 28 x6 y2 + 70 x4 y4 - 28 x2 y6 - y8)     a = 1 + (z8 - 28 z6 w2 + 70 z4 w4 - 28 z2 w6) / w8
+//     Y = 8 a x y (x6 - 7 x4 y2 + 7 x2 y4 - y6)            w2 = x2 + y2
+//     Z = 8 z w (z2 - w2)(z4 - 6 z2 w2 + w4)
+// read as complex 8th powers, which three squarings evaluate:
+//     a w8 = Re (z + i w)^8 =: A,   Z = Im (z + i w)^8,
+//     X = A (cos 8phi - 2 v^8),  Y = A sin 8phi   with (u, v) = (x, y) / w = e^{i phi}
+// (the "- 2 v^8" is the reference's "- y8" where the real part of (x + i y)^8 has "+ y8"; it is
+// reproduced, not fixed).  Working on the unit vector (u, v) removes the division by w^8, which
+// underflows near the z axis and injects inf/NaN into the reference's own arithmetic; w2 is clamped
+// before the rsqrt, so the step is finite for every finite input.
+// 28 FMA-pipe instructions + 1 MUFU per step (+ 4 and 1 MUFU for dr) against 75 algorithmic flops.
+__device__ __forceinline__ void p8_azimuth(float x, float y, float w2, float& iw, float& c8, float& s8h) {
+    iw = fast_rsqrt(fmaxf(w2, 1e-36f));
+    const float u = x * iw, v = y * iw;
+    const float v2 = v * v;
+    const float c2 = fmaf(u, u, -v2);                       // cos 2phi
+    const float s2 = 2.0f * (u * v);                        // sin 2phi
+    const float c4 = fmaf(c2, c2, -(s2 * s2));              // cos 4phi
+    const float q4 = 2.0f * (s2 * c2);                      // sin 4phi
+    const float v4 = v2 * v2;
+    c8 = fmaf(-2.0f, v4 * v4, fmaf(c4, c4, -(q4 * q4)));    // cos 8phi - 2 v^8
+    s8h = c4 * q4;                                          // sin 8phi / 2
+}
+
+__device__ __forceinline__ void p8_elevation(float z, float z2, float w, float w2, float& A, float& Zh) {
+    const float s2 = 2.0f * (z * w);
+    const float c2 = z2 - w2;
+    const float c4 = fmaf(c2, c2, -(s2 * s2));
+    const float q4 = 2.0f * (s2 * c2);
+    A = fmaf(c4, c4, -(q4 * q4));                           // Re (z + i w)^8
+    Zh = c4 * q4;                                           // Im (z + i w)^8 / 2
+}
+
 __device__ __forceinline__ void rotate_p8_fast(float x, float y, float z, float z2, float w2,
                                                float px, float py, float pz, float& ox, float& oy, float& oz) {
-    const float iw = fast_rsqrt(fmaxf(w2, 1e-36f));
-    const float w = w2 * iw;
-    const float u = x * iw, v = y * iw;
-    // elevation part
-    const float z4 = z2 * z2, w4 = w2 * w2;
-    const float S1 = z4 + w4, m1 = z2 * w2;
-    const float A = fmaf(68.0f, m1 * m1, S1 * fmaf(-28.0f, m1, S1));
-    const float Zp = (z * w) * (z2 - w2) * fmaf(-6.0f, m1, S1);
-    // azimuth part on the unit circle
-    const float u2 = u * u, v2 = v * v;
-    const float u4 = u2 * u2, v4 = v2 * v2;
-    const float S2 = u4 + v4, D2 = u4 - v4, m2 = u2 * v2;
-    const float c8 = fmaf(70.0f, m2 * m2, S2 * fmaf(-28.0f, m2, D2));
-    const float s8 = (u * v) * (u2 - v2) * fmaf(-6.0f, m2, S2);
+    float iw, c8, s8h, A, Zh;
+    p8_azimuth(x, y, w2, iw, c8, s8h);
+    p8_elevation(z, z2, w2 * iw, w2, A, Zh);
     ox = fmaf(A, c8, px);
-    oy = fmaf(8.0f * A, s8, py);
-    oz = fmaf(8.0f, Zp, pz);
+    oy = fmaf(2.0f * A, s8h, py);
+    oz = fmaf(2.0f, Zh, pz);
 }
 
 // FAST path for a sample ON the z axis (px == py == 0 exactly): the orbit never leaves the axis
@@ -308,6 +318,34 @@ __device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px,
         }
     } while (--left);
     // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
+    return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
+}
+
+// FAST power-8 DE for a sample of a lattice COLUMN: K1 walks 32 z-samples with (px, py) fixed, so the
+// first iteration's azimuth factors (c8, s8h), w and w2 are computed once per column and only the
+// elevation part of the first step is per sample.  Caller guarantees (px, py) != (0, 0).
+__device__ __forceinline__ float mandelbulb_de_fast_p8_column(const ShapeDev& s, float px, float py, float pz,
+                                                              float w2c, float wc, float c8, float s8h) {
+    const float bail2 = s.bail2;
+    float dr = 1.0f;
+    float r2 = fmaf(pz, pz, w2c);
+    if (!(r2 > bail2)) {
+        const float z2 = pz * pz;
+        const float r6 = r2 * r2 * r2;
+        dr = fmaf(8.0f, r6 * fast_sqrt(r2), 1.0f);           // 8 r^7 * 1 + 1
+        float A, Zh;
+        p8_elevation(pz, z2, wc, w2c, A, Zh);
+        float zx = fmaf(A, c8, px), zy = fmaf(2.0f * A, s8h, py), zz = fmaf(2.0f, Zh, pz);
+        for (uint32_t left = s.max_iters - 1u; left; --left) {
+            const float zz2 = zz * zz;
+            const float w2 = fmaf(zx, zx, zy * zy);
+            r2 = w2 + zz2;
+            if (r2 > bail2) break;
+            const float q6 = r2 * r2 * r2;
+            dr = fmaf(8.0f * (q6 * fast_sqrt(r2)), dr, 1.0f);
+            rotate_p8_fast(zx, zy, zz, zz2, w2, px, py, pz, zx, zy, zz);
+        }
+    }
     return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
 }
 

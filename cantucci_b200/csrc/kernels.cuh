@@ -147,18 +147,29 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         uint32_t word = 0;
         // the fast DE's on-axis special case is tested once per warp, not once per sample
         const bool any_axis = kFast && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
-#define CTC_K1_STEPS(CHECK_AXIS)                                                                   \
+#define CTC_K1_STEPS(DE_EXPR)                                                                      \
         _Pragma("unroll 1")                                                                        \
         for (int j = 0; j < 8; ++j) {                                                              \
             const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));                                   \
-            const float d = shape_de<kFast, kVariant, CHECK_AXIS>(sh, px, py, pz);                 \
+            const float d = DE_EXPR;                                                               \
             *out = d;                                                                              \
             out += 4;                                                                              \
             const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);               \
             word = __funnelshift_r(word, b >> row_shift, 4);   /* nibble j -> bits [4j, 4j+4) */   \
             vz = __fadd_rn(vz, dvz4);                                                              \
         }
-        if (any_axis) { CTC_K1_STEPS(true) } else { CTC_K1_STEPS(false) }
+        if (any_axis) {
+            CTC_K1_STEPS((shape_de<kFast, kVariant, true>(sh, px, py, pz)))
+        } else if (kFast && kVariant == kVarP8) {
+            // (px, py) is fixed along the walk: hoist the first iteration's azimuth factors
+            const float w2c = fmaf(px, px, py * py);
+            float iw, c8, s8h;
+            p8_azimuth(px, py, w2c, iw, c8, s8h);
+            const float wc = w2c * iw;
+            CTC_K1_STEPS((mandelbulb_de_fast_p8_column(sh, px, py, pz, w2c, wc, c8, s8h)))
+        } else {
+            CTC_K1_STEPS((shape_de<kFast, kVariant, false>(sh, px, py, pz)))
+        }
 #undef CTC_K1_STEPS
         if (sign_stride != 0u && (lane & 3u) == 0u && word != 0u) {
             const uint32_t j0 = (x * n + y) * n + (zb << 5);
@@ -308,8 +319,6 @@ classify_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, ui
                 mz |= (uint32_t)(x > 0u && y > 0u && s0 != s1) << b;
             }
         }
-        const size_t o = (size_t)span * words_per_span + word;
-        m.active[o] = ma; m.ex[o] = mx; m.ey[o] = my; m.ez[o] = mz;
     }
     // chunk totals
     uint32_t v = __popc(ma), q = __popc(mx) + __popc(my) + __popc(mz);
@@ -321,11 +330,16 @@ classify_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, ui
     __shared__ uint32_t sv[kThreads / 32], sq[kThreads / 32];
     if ((t & 31u) == 0u) { sv[t >> 5] = v; sq[t >> 5] = q; }
     __syncthreads();
-    if (t == 0) {
-        uint32_t tv = 0, tq = 0;
+    uint32_t tv = 0, tq = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) { tv += sv[w]; tq += sq[w]; }
-        chunk_counts[(size_t)span * gridDim.x + chunk] = make_uint2(tv, tq);
+    for (int w = 0; w < kThreads / 32; ++w) { tv += sv[w]; tq += sq[w]; }
+    if (t == 0) chunk_counts[(size_t)span * gridDim.x + chunk] = make_uint2(tv, tq);
+    // A chunk without an active cell is never looked at again (every quad-owning corner and every
+    // cell a rank query touches is active), so its four mask words per 32 cells are not written:
+    // ~3/4 of the chunks of a typical volume.
+    if (tv != 0u && t < chunk_words) {
+        const size_t o = (size_t)span * words_per_span + chunk * chunk_words + t;
+        m.active[o] = ma; m.ex[o] = mx; m.ey[o] = my; m.ez[o] = mz;
     }
 }
 
@@ -389,11 +403,13 @@ scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ c
 // the compacted list of active cells.  Same grid as E1; one word per thread.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_pre, uint32_t words_per_span, uint32_t chunk_words,
+apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_counts, const uint2* __restrict__ chunk_pre,
+                    uint32_t words_per_span, uint32_t chunk_words,
                     uint32_t lg3 /* log2(R^3) */, uint32_t* __restrict__ word_vpre, uint32_t* __restrict__ word_qpre,
                     uint32_t* __restrict__ cell_of, uint32_t cell_cap) {
     const uint32_t span = blockIdx.y, chunk = blockIdx.x;
     const uint32_t t = threadIdx.x;
+    if (chunk_counts[(size_t)span * gridDim.x + chunk].x == 0u) return;   // no active cell: masks were not written
     const size_t o = (size_t)span * words_per_span + chunk * chunk_words + t;
     uint32_t ma = 0, v = 0, q = 0;
     if (t < chunk_words) {
@@ -427,7 +443,7 @@ apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_pre, uint32_t words
 struct VertexOut { float px, py, pz, nx, ny, nz, d; };
 
 template <bool kFast, int kVariant>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __restrict__ grids, size_t grid_stride,
               uint32_t R, uint32_t lg, const uint32_t* __restrict__ cell_of, uint32_t cell_cap, MeshState* st,
               uint32_t span0, float* __restrict__ out_v, unsigned long long vcap) {
