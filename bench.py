@@ -270,6 +270,13 @@ def ours_main(args):
     t = _lib.CtcTimings()
     _lib.lib().ctc_mesh_result(ctx.handle, None, None, C.byref(t))
     pass_ms[:] = (t.first_ms, t.second_ms, t.third_ms)
+    # the same step once more with strictly serial kernels: per-kernel times without SM sharing
+    serial_ms = np.zeros(3)
+    ctx.set_overlap(False)
+    step(); step()
+    _lib.lib().ctc_mesh_result(ctx.handle, None, None, C.byref(t))
+    serial_ms[:] = (t.first_ms, t.second_ms, t.third_ms)
+    ctx.set_overlap(True)
     tms = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -286,7 +293,9 @@ def ours_main(args):
         ctx.check(_lib.lib().ctc_iteration_stats(ctx.handle, C.byref(sh), sub.ctypes.data, sub.shape[0], RES, stats))
         sum_k, n_bailed, n_s = int(stats[0]), int(stats[1]), int(stats[2])
         flops_pass1 = 75.0 * sum_k + 6.0 * n_bailed + 10.0 * n_s
-        k1_ms = float(pass_ms[0])
+        # pass 1's kernel time: from the serial replay when the timed region overlapped it with the
+        # previous group's extraction (both are reported)
+        k1_ms = float(serial_ms[0])
         achieved = flops_pass1 / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         probe_tf, sms = C.c_double(0.0), C.c_int(0)
@@ -306,7 +315,8 @@ def ours_main(args):
             "frac_of_measured_fma": achieved / probe_tf.value if probe_tf.value else None,
             "algorithmic_flops_per_launch_group": flops_pass1, "mean_iterations_per_sample": sum_k / max(n_s, 1),
             "kernel_ms_per_step": k1_ms,
-            "passes_ms_last_step": {"first_de": pass_ms[0], "second_classify_vertices": pass_ms[1], "third_quads": pass_ms[2]},
+            "passes_ms_timed_region_overlapped": {"first_de": pass_ms[0], "second_classify_vertices": pass_ms[1], "third_quads": pass_ms[2]},
+            "passes_ms_serial_replay": {"first_de": serial_ms[0], "second_classify_vertices": serial_ms[1], "third_quads": serial_ms[2]},
             "hbm_gbs_measured": peaks.get("hbm_gbs"),
         }
         # ---- e2e: host buffers through the public C ABI call (ctc_mesh_spans), copies included ---

@@ -62,7 +62,7 @@ class CtcTimings(C.Structure):
 # every symbol include/cantucci_b200.h declares
 EXPORTS = (
     "ctc_version", "ctc_device_count", "ctc_ctx_create", "ctc_ctx_destroy", "ctc_ctx_set_stream",
-    "ctc_ctx_set_group_spans", "ctc_ctx_synchronize", "ctc_last_error", "ctc_kernel_launches",
+    "ctc_ctx_set_group_spans", "ctc_ctx_set_overlap", "ctc_ctx_synchronize", "ctc_last_error", "ctc_kernel_launches",
     "ctc_de_batch", "ctc_de_batch_device", "ctc_sample_grids", "ctc_sample_grids_device",
     "ctc_mesh_spans", "ctc_mesh_spans_device", "ctc_mesh_result",
     "ctc_iteration_stats", "ctc_fp32_peak_probe",
@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
     L.ctc_ctx_set_stream.argtypes = [vp, vp]
     L.ctc_ctx_set_group_spans.restype = C.c_int
     L.ctc_ctx_set_group_spans.argtypes = [vp, u32]
+    L.ctc_ctx_set_overlap.restype = C.c_int
+    L.ctc_ctx_set_overlap.argtypes = [vp, C.c_int]
     L.ctc_ctx_synchronize.restype = C.c_int
     L.ctc_ctx_synchronize.argtypes = [vp]
     L.ctc_last_error.restype = C.c_char_p
@@ -166,6 +168,9 @@ class Context:
 
     def set_group_spans(self, n: int):
         self.check(lib().ctc_ctx_set_group_spans(self._h, n))
+
+    def set_overlap(self, enable: bool):
+        self.check(lib().ctc_ctx_set_overlap(self._h, 1 if enable else 0))
 
     def synchronize(self):
         self.check(lib().ctc_ctx_synchronize(self._h))

@@ -61,12 +61,18 @@ struct ctc_ctx {
     uint64_t launches = 0;
     uint32_t group_spans = 0;   // 0 = auto
     bool timing = true;
+    bool overlap = true;        // ctc_ctx_set_overlap
 
     // workspace
     DevBuf geom, grids, sign_bits, m_active, m_ex, m_ey, m_ez, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
     DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
     DevBuf pts_in, pts_out;
     PinnedBuf h_geom, h_state, h_tables;
+
+    // extraction (passes 2-3) runs on its own stream so that group g's small, latency-bound kernels
+    // overlap group g+1's DE kernel; grids and sign planes are double-buffered for that
+    cudaStream_t ext_stream = nullptr;
+    std::vector<cudaEvent_t> k1_done, ext_done;
 
     // pipelined device->host copies of the host-pointer mesh call
     cudaStream_t copy_stream = nullptr;
@@ -201,12 +207,12 @@ cudaEvent_t take_event(ctc_ctx* ctx) {
 }
 
 struct PassTimer {
-    ctc_ctx* ctx; int pass; cudaEvent_t a = nullptr;
-    PassTimer(ctc_ctx* c, int p) : ctx(c), pass(p) {
-        if (ctx->timing) { a = take_event(ctx); if (a) cudaEventRecord(a, ctx->stream); }
+    ctc_ctx* ctx; int pass; cudaStream_t st; cudaEvent_t a = nullptr;
+    PassTimer(ctc_ctx* c, int p, cudaStream_t s) : ctx(c), pass(p), st(s) {
+        if (ctx->timing) { a = take_event(ctx); if (a) cudaEventRecord(a, st); }
     }
     ~PassTimer() {
-        if (a) { cudaEvent_t b = take_event(ctx); if (b) { cudaEventRecord(b, ctx->stream); ctx->ev_pairs.push_back({a, b, pass}); } }
+        if (a) { cudaEvent_t b = take_event(ctx); if (b) { cudaEventRecord(b, st); ctx->ev_pairs.push_back({a, b, pass}); } }
     }
 };
 
@@ -290,8 +296,8 @@ int de_batch_impl(ctc_ctx* ctx, const ctc_shape* shape, const float* d_xyz, size
 template <bool kFast, int kVariant>
 void launch_vertex(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, const float* grids, size_t stride, uint32_t R,
                    uint32_t lg, const uint32_t* cell_of, uint32_t cell_cap, MeshState* st, uint32_t span0, float* out_v,
-                   unsigned long long vcap, unsigned blocks) {
-    vertex_kernel<kFast, kVariant><<<blocks, kThreads, 0, ctx->stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap,
+                   unsigned long long vcap, unsigned blocks, cudaStream_t stream) {
+    vertex_kernel<kFast, kVariant><<<blocks, kThreads, 0, stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap,
                                                                          st, span0, out_v, vcap);
     ctx->launches++;
 }
@@ -338,12 +344,14 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     const size_t words = G * gp.words_per_span, chunks = G * gp.chunks_per_span;
     const size_t group_cells = G * ((size_t)R * R * R);
     const uint32_t cell_cap = (uint32_t)(group_cells < vcap ? group_cells : (vcap < 0xFFFFFFFFull ? vcap : 0xFFFFFFFFull));
-    CK(ctx->grids.ensure(G * gp.n3 * sizeof(float)));
+    // more than one group: overlap extraction(g) with DE(g+1)
+    const bool two_streams = (nspans > G) && ctx->overlap;
+    const size_t nbuf = two_streams ? 2 : 1;
+    CK(ctx->grids.ensure(nbuf * G * gp.n3 * sizeof(float)));
     CK(ctx->m_active.ensure(words * 4)); CK(ctx->m_ex.ensure(words * 4)); CK(ctx->m_ey.ensure(words * 4));
     CK(ctx->m_ez.ensure(words * 4));
     const uint32_t sign_stride = (uint32_t)((gp.n3 + 31) / 32 + 1);
-    CK(ctx->sign_bits.ensure(G * (size_t)sign_stride * 4));
-    uint32_t* sign_bits = ctx->sign_bits.as<uint32_t>();
+    CK(ctx->sign_bits.ensure(nbuf * G * (size_t)sign_stride * 4));
     CK(ctx->word_vpre.ensure(words * 4)); CK(ctx->word_qpre.ensure(words * 4));
     CK(ctx->chunk_counts.ensure(chunks * sizeof(uint2))); CK(ctx->chunk_pre.ensure(chunks * sizeof(uint2)));
     CK(ctx->cell_of.ensure((size_t)(cell_cap ? cell_cap : 1) * 4));
@@ -351,9 +359,28 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
 
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
     const int variant = shape_variant(shape);
-    float* grids = ctx->grids.as<float>();
     const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
     const size_t n_groups = (nspans + G - 1) / G;
+    cudaStream_t sA = ctx->stream, sE = ctx->stream;
+    if (two_streams) {
+        if (!ctx->ext_stream) {
+            // highest priority: the short extraction kernels take SM slots as the long DE kernel's CTAs retire
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&ctx->ext_stream, cudaStreamNonBlocking, hi));
+        }
+        sE = ctx->ext_stream;
+        while (ctx->k1_done.size() < n_groups) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            ctx->k1_done.push_back(a); ctx->ext_done.push_back(b);
+        }
+        // the extraction stream starts after everything already enqueued on the caller's stream
+        // (state reset, geometry upload)
+        CK(cudaEventRecord(ctx->k1_done[0], sA));
+        CK(cudaStreamWaitEvent(sE, ctx->k1_done[0], 0));
+    }
     if (pipeline) {
         rc = ensure_progress(ctx, n_groups); if (rc) return rc;
         while (ctx->group_events.size() < n_groups) {
@@ -365,45 +392,56 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
 
     for (size_t s0 = 0; s0 < nspans; s0 += G) {
         const size_t gi = s0 / G;
+        float* grids = ctx->grids.as<float>() + (gi % nbuf) * G * gp.n3;
+        uint32_t* sign_bits = ctx->sign_bits.as<uint32_t>() + (gi % nbuf) * G * (size_t)sign_stride;
+        // this buffer pair was last read by the extraction of group gi-2
+        if (two_streams && gi >= 2) CK(cudaStreamWaitEvent(sA, ctx->ext_done[gi - 2], 0));
         const uint32_t cnt = (uint32_t)((nspans - s0) < G ? (nspans - s0) : G);
         const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
         {   // pass 1
-            PassTimer t(ctx, 0);
-            CK(cudaMemsetAsync(sign_bits, 0, (size_t)cnt * sign_stride * 4, ctx->stream));
+            PassTimer t(ctx, 0, sA);
+            CK(cudaMemsetAsync(sign_bits, 0, (size_t)cnt * sign_stride * 4, sA));
 #define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3, sign_bits, sign_stride)
             DISPATCH(fast, variant, CALL);
 #undef CALL
         }
+        if (two_streams) {
+            CK(cudaEventRecord(ctx->k1_done[gi], sA));
+            CK(cudaStreamWaitEvent(sE, ctx->k1_done[gi], 0));
+        }
         dim3 cgrid(gp.chunks_per_span, cnt);
         {   // pass 2: classify, scan, vertices
-            PassTimer t(ctx, 1);
-            classify_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
+            PassTimer t(ctx, 1, sE);
+            classify_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
                                                                 gp.chunk_words, m, ctx->chunk_counts.as<uint2>());
-            scan_chunks_kernel<<<1, kScanThreads, 0, ctx->stream>>>(
+            scan_chunks_kernel<<<1, kScanThreads, 0, sE>>>(
                 ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
                 (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
                 reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st,
                 pipeline ? ctx->progress_d + 2 * gi : nullptr);
-            apply_prefix_kernel<<<cgrid, kThreads, 0, ctx->stream>>>(m, ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), gp.words_per_span,
+            apply_prefix_kernel<<<cgrid, kThreads, 0, sE>>>(m, ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), gp.words_per_span,
                                                                     gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
                                                                     ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
                                                                     cell_cap);
             ctx->launches += 3;
 #define CALL(F, V) launch_vertex<F, V>(ctx, sh, geom, grids, gp.n3, R, lg, ctx->cell_of.as<uint32_t>(), cell_cap, st, \
-                                       (uint32_t)s0, reinterpret_cast<float*>(d_v), (unsigned long long)vcap, vblocks)
+                                       (uint32_t)s0, reinterpret_cast<float*>(d_v), (unsigned long long)vcap, vblocks, sE)
             DISPATCH(fast, variant, CALL);
 #undef CALL
         }
         {   // pass 3
-            PassTimer t(ctx, 2);
-            quad_kernel<<<vblocks, kThreads, 0, ctx->stream>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
+            PassTimer t(ctx, 2, sE);
+            quad_kernel<<<vblocks, kThreads, 0, sE>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
                                                               grids, gp.n3, R, lg, gp.words_per_span,
                                                               ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
                                                               (unsigned long long)icap);
             ctx->launches++;
         }
-        if (pipeline) CK(cudaEventRecord(ctx->group_events[gi], ctx->stream));
+        if (pipeline) CK(cudaEventRecord(ctx->group_events[gi], sE));
+        if (two_streams) CK(cudaEventRecord(ctx->ext_done[gi], sE));
     }
+    // the caller's stream owns completion: it joins the extraction stream
+    if (two_streams) CK(cudaStreamWaitEvent(sA, ctx->ext_done[n_groups - 1], 0));
     ctx->n_groups = pipeline ? n_groups : 0;
     CK(cudaGetLastError());
     return CTC_OK;
@@ -484,6 +522,9 @@ void ctc_ctx_destroy(ctc_ctx* c) {
     c->h_geom.release(); c->h_state.release(); c->h_tables.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->k1_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ext_done) cudaEventDestroy(e);
+    if (c->ext_stream) cudaStreamDestroy(c->ext_stream);
     if (c->progress_h) cudaFreeHost(c->progress_h);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -503,6 +544,13 @@ int ctc_ctx_set_group_spans(ctc_ctx* ctx, uint32_t spans_per_group) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->group_spans = spans_per_group;
+    return CTC_OK;
+}
+
+int ctc_ctx_set_overlap(ctc_ctx* ctx, int enable) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->overlap = enable != 0;
     return CTC_OK;
 }
 

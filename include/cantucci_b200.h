@@ -114,6 +114,10 @@ CTC_API int ctc_ctx_set_stream(ctc_ctx *ctx, void *cuda_stream);
 /* Spans per internal launch group (0 = automatic, sized to keep a group's
  * sample grids L2-resident). */
 CTC_API int ctc_ctx_set_group_spans(ctc_ctx *ctx, uint32_t spans_per_group);
+/* 1 (default): a launch group's extraction kernels run on a second, high-
+ * priority stream concurrently with the next group's DE kernel.  0: strictly
+ * serial kernels (per-pass timings then do not overlap; used for profiling). */
+CTC_API int ctc_ctx_set_overlap(ctc_ctx *ctx, int enable);
 CTC_API int ctc_ctx_synchronize(ctc_ctx *ctx);
 /* Human-readable description of the last failure on this context. */
 CTC_API const char *ctc_last_error(const ctc_ctx *ctx);
