@@ -363,8 +363,8 @@ def ours_main(args):
                                        + ("" if world == 1 else (" by one-sided puts into rank 0's IPC-mapped buffers (copy engines "
                                           "over NVLink, pipelined behind compute)" if args.gather == "peer"
                                           else " by grouped NCCL send/recv"))),
-                       "l2": "per-step working set (4.5 GB of sample grids streamed in 64 MiB groups + 0.7 GB of mesh) "
-                             "exceeds the 126 MB L2; no explicit flush"},
+                       "l2": "per-step working set (4.5 GB of sample grids streamed in 512 MiB launch groups + 0.7 GB of "
+                             "mesh per volume) exceeds the 126 MB L2; no explicit flush"},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
             "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * 4),
             "gpu_launches": int(launches2 - launches1),

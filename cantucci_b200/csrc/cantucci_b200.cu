@@ -75,7 +75,7 @@ struct ctc_ctx {
     std::vector<cudaEvent_t> k1_done, ext_done;
 
     // pipelined device->host copies of the host-pointer mesh call
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;   // vertices / indices
     unsigned long long* progress_h = nullptr;     // mapped pinned: totals after each group
     unsigned long long* progress_d = nullptr;
     size_t progress_cap = 0;                      // groups
@@ -527,6 +527,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
     if (c->ext_stream) cudaStreamDestroy(c->ext_stream);
     if (c->progress_h) cudaFreeHost(c->progress_h);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -646,6 +647,7 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
     CK(ctx->out_idx.ensure((icap ? icap : 1) * sizeof(uint32_t)));
     CK(ctx->off_v.ensure((nspans + 1) * 8)); CK(ctx->off_i.ensure((nspans + 1) * 8));
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_stream2) CK(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
     int rc = mesh_spans_impl(ctx, shape, spans, nspans, resolution, ctx->out_v.as<ctc_vertex>(), vcap,
                              ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
                              /*pipeline=*/true);
@@ -682,11 +684,12 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
         }
         if (ci > done_i) {
             CK(cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
-                               cudaMemcpyDefault, ctx->copy_stream));
+                               cudaMemcpyDefault, ctx->copy_stream2));
             done_i = ci;
         }
     }
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream2));
     uint64_t nv = 0, ni = 0;
     const int status = mesh_result_impl(ctx, &nv, &ni, timings, /*state_already_copied=*/true);   // syncs the compute stream
     if (status != CTC_ERR_CUDA && !tables_on_device) {
