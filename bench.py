@@ -225,13 +225,13 @@ def ours_main(args):
         dist.all_reduce(tot)
     nv_tot, ni_tot = int(tot[0]), int(tot[1])
     pad = lambda n: int(n * 1.02) + 1024
-    if world > 1 and args.gather == "peer":
+    if world > 1 and args.gather in ("peer", "direct"):
         caps = torch.zeros((world, 2), dtype=torch.int64, device=device)
         caps[rank, 0], caps[rank, 1] = pad(nv_loc), pad(ni_loc)
         dist.all_reduce(caps)
         caps = caps.cpu().numpy()
         sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
-                                    mode="block")
+                                    mode="block", direct=(args.gather == "direct"))
     else:
         mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
         sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode="block")
@@ -386,8 +386,9 @@ def main():
     ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic instead of the fast mode")
     ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N>1: one-sided puts into rank 0's IPC-mapped buffers (default) or NCCL send/recv")
+    ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],
+                    help="N>1: copy-engine puts into rank 0's IPC-mapped buffers (default), kernels storing "
+                         "straight into them (direct), or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -176,9 +176,12 @@ class PeerGatherScheduler:
     offset tables.  One barrier per step tells rank 0 that every put has landed."""
 
     def __init__(self, dist, torch, ctx: _lib.Context, rank: int, world: int, device, nspans: int,
-                 caps_v: list, caps_i: list, mode: str = "interleave"):
+                 caps_v: list, caps_i: list, mode: str = "interleave", direct: bool = False):
+        """direct = False: ranks > 0 mesh into local buffers and the copy engines put each launch group's
+        slice into rank 0's region (pipelined).  direct = True: the vertex / quad / scan kernels of
+        ranks > 0 store straight into rank 0's mapped region -- compute and gather are one kernel."""
         self.dist, self.torch, self.ctx, self.rank, self.world, self.device = dist, torch, ctx, rank, world, device
-        self.nspans, self.mode = nspans, mode
+        self.nspans, self.mode, self.direct = nspans, mode, direct
         self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
         self.n_r = [len(x) for x in self.shards]
         self.caps_v = [int(c) for c in caps_v]
@@ -234,9 +237,9 @@ class PeerGatherScheduler:
         if local is None:
             local = np.ascontiguousarray(spans[self.shards[rank]])
         pv, pi, tv, ti = self._region(rank)
-        if rank == 0:
+        if rank == 0 or self.direct:
             ctx.check(L.ctc_mesh_spans_device(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0],
-                                              resolution, pv, self.caps_v[0], pi, self.caps_i[0], tv, ti))
+                                              resolution, pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti))
             rc = L.ctc_mesh_result(ctx.handle, None, None, None)
         else:
             rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,

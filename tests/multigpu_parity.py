@@ -44,13 +44,18 @@ cap_v, cap_i = 400_000, 2_400_000
 mesher = DeviceMesher(ctx, torch, device, cap_v, cap_i, len(mine))
 nccl = SpanScheduler(dist, torch, rank, world, device, mesher, cap_v * world, cap_i * world)
 peer = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world)
+direct = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
+                             direct=True)
 for _ in range(2):
     g1 = nccl.run(sh, spans, R)
     g2 = peer.run(sh, spans, R)
+    g3 = direct.run(sh, spans, R)
 if rank == 0:
     check(g1, "nccl")
     check(g2, "peer")
+    check(g3, "direct")
     print("MULTIGPU_PARITY_OK", world, g2.n_vertices, g2.n_indices, flush=True)
 dist.barrier()
 peer.close()
+direct.close()
 dist.destroy_process_group()
