@@ -184,8 +184,9 @@ class PeerGatherScheduler:
         self.nspans, self.mode, self.direct = nspans, mode, direct
         self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
         self.n_r = [len(x) for x in self.shards]
-        self.caps_v = [int(c) for c in caps_v]
-        self.caps_i = [int(c) for c in caps_i]
+        # regions start on 256-byte boundaries (the kernels store 8-byte index pairs)
+        self.caps_v = [(int(c) + 63) // 64 * 64 for c in caps_v]
+        self.caps_i = [(int(c) + 63) // 64 * 64 for c in caps_i]
         self.base_v = np.concatenate([[0], np.cumsum(self.caps_v)]).astype(np.int64)      # in vertices
         self.base_i = np.concatenate([[0], np.cumsum(self.caps_i)]).astype(np.int64)      # in indices
         self.base_t = np.concatenate([[0], np.cumsum([n + 1 for n in self.n_r])]).astype(np.int64)   # table entries
