@@ -200,6 +200,8 @@ def ours_main(args):
     ctx = cb.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    if args.group_spans:
+        ctx.set_group_spans(args.group_spans)
 
     fast = not args.exact
     shape = cb.Mandelbulb.classic(MAX_ITERS, BAILOUT, fast=fast)
@@ -386,6 +388,7 @@ def main():
     ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic instead of the fast mode")
     ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
     ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],
                     help="N>1: copy-engine puts into rank 0's IPC-mapped buffers (default), kernels storing "
                          "straight into them (direct), or NCCL send/recv")

@@ -360,7 +360,20 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
     const int variant = shape_variant(shape);
     const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
-    const size_t n_groups = (nspans + G - 1) / G;
+    // Launch groups.  With the copy pipeline on, the first groups are small (64, 128, 256, ... spans)
+    // so that the device->host / peer copies start almost immediately instead of after a full group.
+    std::vector<std::pair<size_t, uint32_t>> groups;
+    {
+        size_t s0 = 0, ramp = 64;
+        while (s0 < nspans) {
+            size_t cnt = G;
+            if (pipeline && ctx->group_spans == 0 && ramp < G) { cnt = ramp; ramp *= 2; }
+            if (cnt > nspans - s0) cnt = nspans - s0;
+            groups.emplace_back(s0, (uint32_t)cnt);
+            s0 += cnt;
+        }
+    }
+    const size_t n_groups = groups.size();
     cudaStream_t sA = ctx->stream, sE = ctx->stream;
     if (two_streams) {
         if (!ctx->ext_stream) {
@@ -390,13 +403,13 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         }
     }
 
-    for (size_t s0 = 0; s0 < nspans; s0 += G) {
-        const size_t gi = s0 / G;
+    for (size_t gi = 0; gi < n_groups; ++gi) {
+        const size_t s0 = groups[gi].first;
         float* grids = ctx->grids.as<float>() + (gi % nbuf) * G * gp.n3;
         uint32_t* sign_bits = ctx->sign_bits.as<uint32_t>() + (gi % nbuf) * G * (size_t)sign_stride;
         // this buffer pair was last read by the extraction of group gi-2
         if (two_streams && gi >= 2) CK(cudaStreamWaitEvent(sA, ctx->ext_done[gi - 2], 0));
-        const uint32_t cnt = (uint32_t)((nspans - s0) < G ? (nspans - s0) : G);
+        const uint32_t cnt = groups[gi].second;
         const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
         {   // pass 1
             PassTimer t(ctx, 0, sA);
