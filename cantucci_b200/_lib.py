@@ -66,7 +66,7 @@ EXPORTS = (
     "ctc_de_batch", "ctc_de_batch_device", "ctc_sample_grids", "ctc_sample_grids_device",
     "ctc_mesh_spans", "ctc_mesh_spans_device", "ctc_mesh_result",
     "ctc_iteration_stats", "ctc_fp32_peak_probe",
-    "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
+    "ctc_ray_march", "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
 )
 
 _lib = None
@@ -125,6 +125,8 @@ def lib() -> C.CDLL:
     L.ctc_mesh_result.argtypes = [vp, u64p, u64p, C.POINTER(CtcTimings)]
     L.ctc_iteration_stats.restype = C.c_int
     L.ctc_iteration_stats.argtypes = [vp, shp, spn, sz, u32, u64p]
+    L.ctc_ray_march.restype = C.c_int
+    L.ctc_ray_march.argtypes = [vp, shp, vp, vp, sz, u32, C.c_float, vp, vp]
     L.ctc_device_alloc.restype = C.c_int
     L.ctc_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     L.ctc_device_free.restype = C.c_int

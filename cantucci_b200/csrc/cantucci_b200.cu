@@ -712,6 +712,34 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
     return status;
 }
 
+int ctc_ray_march(ctc_ctx* ctx, const ctc_shape* shape, const float* origin, const float* dir, size_t n,
+                  uint32_t max_steps, float epsilon, float* out_pos, uint32_t* out_hit) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    if (n == 0) return CTC_OK;
+    if (!origin || !dir || !out_pos || !out_hit) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL ray buffer");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->pts_in.ensure(n * 24)); CK(ctx->pts_out.ensure(n * 16));
+    float* d_o = ctx->pts_in.as<float>(); float* d_d = d_o + 3 * n;
+    float* d_p = ctx->pts_out.as<float>(); uint32_t* d_h = reinterpret_cast<uint32_t*>(d_p + 3 * n);
+    CK(cudaMemcpyAsync(d_o, origin, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_d, dir, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
+    const int variant = shape_variant(shape);
+    const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+#define CALL(F, V) ray_march_kernel<F, V><<<blocks, kThreads, 0, ctx->stream>>>(sh, d_o, d_d, n, max_steps, epsilon, d_p, d_h)
+    DISPATCH(fast, variant, CALL);
+#undef CALL
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_pos, d_p, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_hit, d_h, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CTC_OK;
+}
+
 int ctc_device_alloc(ctc_ctx* ctx, size_t bytes, void** d_ptr) {
     if (!ctx || !d_ptr) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);

@@ -594,6 +594,33 @@ quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------
+// N1: sphere tracing of the focus rays, ShapeMesh::get_focii
+// (mesh/mod.rs:229-241).  One thread per ray:
+//     for _ in 0..MAX_ITERS { d = DE(pos); pos += dir * d; if d < EPSILON { return Some(pos) } }
+// hit[i] = 1 and out[i] = pos on success, hit[i] = 0 otherwise.  Arithmetic of the march itself
+// (pos += dir * d) is exact-order; the DE follows the shape's math mode.
+// ---------------------------------------------------------------------------
+template <bool kFast, int kVariant>
+__global__ void __launch_bounds__(kThreads)
+ray_march_kernel(ShapeDev sh, const float* __restrict__ origin, const float* __restrict__ dir, size_t n,
+                 uint32_t max_steps, float epsilon, float* __restrict__ out, uint32_t* __restrict__ hit) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float px = origin[3 * i], py = origin[3 * i + 1], pz = origin[3 * i + 2];
+    const float dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+    uint32_t ok = 0;
+    for (uint32_t s = 0; s < max_steps; ++s) {
+        const float d = shape_de<kFast, kVariant>(sh, px, py, pz);
+        px = __fadd_rn(px, __fmul_rn(dx, d));
+        py = __fadd_rn(py, __fmul_rn(dy, d));
+        pz = __fadd_rn(pz, __fmul_rn(dz, d));
+        if (d < epsilon) { ok = 1; break; }
+    }
+    out[3 * i] = px; out[3 * i + 1] = py; out[3 * i + 2] = pz;
+    hit[i] = ok;
+}
+
+// ---------------------------------------------------------------------------
 // Measurement aids (not on the hot path).
 // ---------------------------------------------------------------------------
 // Completed iterations and bail-outs over the sample lattices of a span batch (EXACT arithmetic,

@@ -63,6 +63,17 @@ def get_focii(shape: Shape, camera: Camera, focus_points: int = FOCUS_POINTS, ct
     dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
     pos = np.repeat(camera.position[None, :], len(pts), axis=0).astype(np.float32)
     dirs = dirs.astype(np.float32)
+    if type(shape).batch_min_distance_from is Shape.batch_min_distance_from:
+        # the CUDA shape: all rays are sphere-traced in one kernel launch (ctc_ray_march)
+        import ctypes as C
+        from . import _lib
+        ctx = ctx or _lib.default_context()
+        pos = np.ascontiguousarray(pos); dirs = np.ascontiguousarray(dirs)
+        out = np.empty_like(pos); hit = np.zeros(len(pts), dtype=np.uint32)
+        sh = shape._ctc_shape()
+        ctx.check(_lib.lib().ctc_ray_march(ctx.handle, C.byref(sh), pos.ctypes.data, dirs.ctypes.data, len(pts),
+                                           MAX_ITERS, EPSILON, out.ctypes.data, hit.ctypes.data))
+        return out[hit != 0]
     done = np.zeros(len(pts), dtype=bool)
     for _ in range(MAX_ITERS):
         live = ~done

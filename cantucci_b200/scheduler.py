@@ -280,6 +280,17 @@ class LazyGather:
             self._built = (span_v, span_i, nv, ni)
         return self._built
 
+    def regions(self):
+        """[(first vertex, vertex count, first index, index count)] of every rank's region."""
+        s = self._s
+        nt = int(s.base_t[-1])
+        out = []
+        for r in range(s.world):
+            nv = int(self._tables[s.base_t[r + 1] - 1])
+            ni = int(self._tables[nt + s.base_t[r + 1] - 1])
+            out.append((int(s.base_v[r]), nv, int(s.base_i[r]), ni))
+        return out
+
     span_v = property(lambda self: self._build()[0])
     span_i = property(lambda self: self._build()[1])
     n_vertices = property(lambda self: self._build()[2])

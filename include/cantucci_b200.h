@@ -170,6 +170,15 @@ CTC_API int ctc_mesh_spans_device(ctc_ctx *ctx, const ctc_shape *shape, const ct
  * Returns CTC_OK, CTC_ERR_OVERFLOW or CTC_ERR_LERP_ASSERT. */
 CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indices, ctc_timings *timings);
 
+/* ---- focus rays: ShapeMesh::get_focii's sphere tracing (src/mesh/mod.rs:229-241) ---- */
+
+/* n rays (origin, unit direction; packed xyz, HOST pointers).  Each ray repeats
+ * `d = DE(pos); pos += dir * d; if d < epsilon { hit }` up to max_steps times
+ * (the reference uses EPSILON = 1e-6, MAX_ITERS = 100).  out_pos: n packed xyz,
+ * out_hit: n u32 (1 = Some(pos), 0 = None). */
+CTC_API int ctc_ray_march(ctc_ctx *ctx, const ctc_shape *shape, const float *origin, const float *dir, size_t n,
+                          uint32_t max_steps, float epsilon, float *out_pos, uint32_t *out_hit);
+
 /* ---- peer memory for the multi-GPU gather -------------------------------- */
 
 /* Plain cudaMalloc/cudaFree on the context's device (IPC handles need the base

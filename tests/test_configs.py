@@ -57,6 +57,20 @@ def test_config3_every_leaf_matches_oracle(oracle, ctx):
     assert abs(len(fast.vertices) - len(batch.vertices)) <= len(batch.vertices) // 2000 + 8
 
 
+@pytest.mark.gpu
+def test_ray_march_kernel_matches_host_loop(oracle, ctx):
+    """ctc_ray_march (get_focii's sphere tracing, mesh/mod.rs:229-241) against the same loop on the host
+    with the oracle's DE: exact mode is bit-identical, misses are reported as None."""
+    bulb = cb.Mandelbulb.classic(6, 2.5)
+    cam = refine.Camera.default_orbit()
+    got = refine.get_focii(bulb, cam, 5, ctx)
+    want = refine.get_focii(_OracleBulb.classic(6, 2.5), cam, 5)
+    assert len(got) == len(want) == 25
+    assert np.array_equal(bits(got), bits(want))
+    away = refine.Camera(np.array([-3.0, 0.0, 0.0]), np.array([-1.0, 0.0, 0.0]))     # looking away: no hits
+    assert len(refine.get_focii(bulb, away, 3, ctx)) == 0
+
+
 # ------------------------------------------------------------------ config 4 (power sweep) ---------
 def _tiles16():
     return cb.tile_volume(cb.Span((-1.2, -1.2, -1.2), (1.2, 1.2, 1.2)), 16)
