@@ -785,6 +785,22 @@ int ctc_ipc_close(ctc_ctx* ctx, void* d_ptr) {
     return CTC_OK;
 }
 
+int ctc_host_register(ctc_ctx* ctx, void* ptr, size_t bytes) {
+    if (!ctx || !ptr) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return CTC_OK;
+}
+
+int ctc_host_unregister(ctc_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(ptr));
+    return CTC_OK;
+}
+
 int ctc_iteration_stats(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
                         uint64_t out[3]) {
     if (!ctx || !out) return CTC_ERR_INVALID_ARGUMENT;

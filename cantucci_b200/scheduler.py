@@ -295,3 +295,100 @@ class LazyGather:
     span_i = property(lambda self: self._build()[1])
     n_vertices = property(lambda self: self._build()[2])
     n_indices = property(lambda self: self._build()[3])
+
+
+# ---------------------------------------------------------------------------
+# Host gather: every rank writes its meshes into ONE shared host buffer over its own PCIe link
+# ---------------------------------------------------------------------------
+class HostGatherScheduler:
+    """End-to-end variant for host consumers: the destination is a POSIX shared-memory segment
+    (`/dev/shm`) that every rank maps; each rank page-locks ITS region and passes it to
+    `ctc_mesh_spans`, so the device->host copies of the N ranks run in parallel over N PCIe links
+    (instead of funnelling N volumes through rank 0's single link after an NVLink gather).  Rank 0
+    reads every rank's offset tables straight from the shared segment."""
+
+    def __init__(self, dist, ctx: _lib.Context, rank: int, world: int, nspans: int, caps_v: list, caps_i: list,
+                 mode: str = "interleave", name: str | None = None):
+        import mmap
+        import os
+        self.dist, self.ctx, self.rank, self.world, self.nspans, self.mode = dist, ctx, rank, world, nspans, mode
+        self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
+        self.n_r = [len(x) for x in self.shards]
+        self.caps_v = [(int(c) + 63) // 64 * 64 for c in caps_v]
+        self.caps_i = [(int(c) + 63) // 64 * 64 for c in caps_i]
+        self.base_v = np.concatenate([[0], np.cumsum(self.caps_v)]).astype(np.int64)
+        self.base_i = np.concatenate([[0], np.cumsum(self.caps_i)]).astype(np.int64)
+        self.base_t = np.concatenate([[0], np.cumsum([n + 1 for n in self.n_r])]).astype(np.int64)
+        page = 4096
+        al = lambda n: (int(n) + page - 1) // page * page
+        self.off_v = 0
+        self.off_i = al(int(self.base_v[-1]) * 28)
+        self.off_t = self.off_i + al(int(self.base_i[-1]) * 4)
+        self.total = self.off_t + al(2 * int(self.base_t[-1]) * 8)
+        names = [name or f"/dev/shm/cantucci_b200_gather_{os.getpid()}"]
+        if world > 1:
+            dist.broadcast_object_list(names, src=0)
+        self.path = names[0]
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.total)
+        if world > 1:
+            dist.barrier()
+        self._f = open(self.path, "r+b")
+        self._mm = mmap.mmap(self._f.fileno(), self.total)
+        self.buf = np.frombuffer(self._mm, dtype=np.uint8)
+        self._base = self.buf.ctypes.data
+        # page-lock this rank's three regions (page-aligned supersets)
+        self._pinned = []
+        for lo, hi in ((self.off_v + int(self.base_v[rank]) * 28, self.off_v + int(self.base_v[rank + 1]) * 28),
+                       (self.off_i + int(self.base_i[rank]) * 4, self.off_i + int(self.base_i[rank + 1]) * 4),
+                       (self.off_t, self.total)):
+            lo_p, hi_p = lo // page * page, al(hi)
+            ptr = self._base + lo_p
+            if _lib.lib().ctc_host_register(ctx.handle, C.c_void_p(ptr), hi_p - lo_p) == _lib.CTC_OK:
+                self._pinned.append(ptr)
+
+    def close(self):
+        for ptr in self._pinned:
+            _lib.lib().ctc_host_unregister(self.ctx.handle, C.c_void_p(ptr))
+        self._pinned = []
+        self.buf = None
+        try:
+            self._mm.close(); self._f.close()
+        except Exception:
+            pass
+        if self.rank == 0:
+            import os
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+    def run(self, shape_struct, spans: np.ndarray, resolution: int, local: np.ndarray | None = None):
+        L, ctx, rank = _lib.lib(), self.ctx, self.rank
+        if local is None:
+            local = np.ascontiguousarray(spans[self.shards[rank]])
+        nt = int(self.base_t[-1])
+        pv = self._base + self.off_v + int(self.base_v[rank]) * 28
+        pi = self._base + self.off_i + int(self.base_i[rank]) * 4
+        tv = self._base + self.off_t + int(self.base_t[rank]) * 8
+        ti = self._base + self.off_t + (nt + int(self.base_t[rank])) * 8
+        rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
+                              pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti, None)
+        ctx.check(rc)
+        if self.world > 1:
+            self.dist.barrier()
+        if rank != 0:
+            return None
+        tables = self.buf[self.off_t: self.off_t + 2 * nt * 8].view(np.int64)
+        vertices = self.buf[self.off_v: self.off_v + int(self.base_v[-1]) * 28].view(np.float32).reshape(-1, 7)
+        indices = self.buf[self.off_i: self.off_i + int(self.base_i[-1]) * 4].view(np.uint32)
+        return HostGather(self, tables, vertices, indices)
+
+
+class HostGather(LazyGather):
+    """Rank 0's host-side view of the shared segment (numpy arrays, no copies)."""
+
+    def __init__(self, sched, tables, vertices, indices):
+        self._s, self._tables, self._built = sched, tables, None
+        self.vertices, self.indices = vertices, indices

@@ -195,6 +195,11 @@ CTC_API int ctc_ipc_export(ctc_ctx *ctx, const void *d_ptr, unsigned char handle
 CTC_API int ctc_ipc_open(ctc_ctx *ctx, const unsigned char handle[64], void **d_ptr);
 CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
 
+/* Page-lock / unlock host memory the caller owns (cudaHostRegister, portable), e.g. a POSIX shared-
+ * memory segment that several one-GPU processes fill with ctc_mesh_spans, each over its own PCIe link. */
+CTC_API int ctc_host_register(ctc_ctx *ctx, void *ptr, size_t bytes);
+CTC_API int ctc_host_unregister(ctc_ctx *ctx, void *ptr);
+
 /* ---- measurement aids (not part of the reference's interface) ------------- */
 
 /* Iteration statistics of the sample lattices (exact arithmetic == the

@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cantucci_b200 as cb
-from cantucci_b200.scheduler import DeviceMesher, PeerGatherScheduler, SpanScheduler, shard_indices
+from cantucci_b200.scheduler import DeviceMesher, HostGatherScheduler, PeerGatherScheduler, SpanScheduler, shard_indices
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -30,8 +30,9 @@ if rank == 0:
 
 
 def check(got, name):
-    v = got.vertices.cpu().numpy().view(np.uint32)
-    i = got.indices.cpu().numpy().view(np.uint32)
+    tonp = lambda a: a if isinstance(a, np.ndarray) else a.cpu().numpy()
+    v = tonp(got.vertices).view(np.uint32)
+    i = tonp(got.indices).view(np.uint32)
     assert got.n_vertices == len(ref.vertices) and got.n_indices == len(ref.indices), name
     for s in range(len(spans)):
         a, b = got.span_v[s]; c, d = got.span_i[s]
@@ -46,16 +47,20 @@ nccl = SpanScheduler(dist, torch, rank, world, device, mesher, cap_v * world, ca
 peer = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world)
 direct = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
                              direct=True)
+host = HostGatherScheduler(dist, ctx, rank, world, len(spans), [cap_v] * world, [cap_i] * world)
 for _ in range(2):
     g1 = nccl.run(sh, spans, R)
     g2 = peer.run(sh, spans, R)
     g3 = direct.run(sh, spans, R)
+    g4 = host.run(sh, spans, R)
 if rank == 0:
     check(g1, "nccl")
     check(g2, "peer")
     check(g3, "direct")
+    check(g4, "host")
     print("MULTIGPU_PARITY_OK", world, g2.n_vertices, g2.n_indices, flush=True)
 dist.barrier()
 peer.close()
 direct.close()
+host.close()
 dist.destroy_process_group()
