@@ -387,6 +387,32 @@ def ours_main(args):
             cpu = {"value": r["samples"] / r["secs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                    "sample": f"{r['spans']} of {nspans} spans (tiles with (ix+3iy+5iz)%stride==0), {r['secs']:.2f} s",
                    "span_meshes_per_s": r["spans"] / r["secs"]}
+        # ---- the other BASELINE.json configs, briefly (N = 1 only; parity for them lives in tests/) ---------
+        other = None
+        if world == 1 and args.tiles == TILES:
+            other = {}
+
+            def timed(fn, reps):
+                fn(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b.record(stream); torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+            # config 1: the 64 startup leaves (mesh/mod.rs:52-56), device-resident
+            startup = cb.spans_array([n.span for n in cb.startup_tree(shape.bounding_box()).leaves()])
+            m1 = DeviceMesher(ctx, torch, device, 700_000, 4_200_000, 64)
+            ms1 = timed(lambda: (m1.launch(sh, startup, RES), m1.result()), 20)
+            other["config1_startup_octree_64_spans_R64"] = {"ms": ms1, "samples_per_s": 64 * n3 / (ms1 * 1e-3),
+                                                            "span_meshes_per_s": 64 / (ms1 * 1e-3)}
+            # config 2: dense 512^3 DE sample grid, one bbox span (pass 1 only: meshing this span panics in the reference)
+            bbox = np.array([[-1.2, -1.2, -1.2, 1.2, 1.2, 1.2]], dtype=np.float32)
+            g512 = torch.empty((513 ** 3,), dtype=torch.float32, device=device)
+            ms2 = timed(lambda: ctx.check(_lib.lib().ctc_sample_grids_device(ctx.handle, C.byref(sh), bbox.ctypes.data, 1, 512,
+                                                                             g512.data_ptr())), 10)
+            other["config2_dense_512cube_de_grid_one_span"] = {"ms": ms2, "samples_per_s": 513 ** 3 / (ms2 * 1e-3)}
+            del g512, m1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -403,7 +429,7 @@ def ours_main(args):
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
             "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * 4),
             "gpu_launches": int(launches2 - launches1),
-            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
