@@ -1,14 +1,16 @@
 // kernels.cuh -- the hot-path kernels (sm_100a).
 //
-//   K1  sample_grids_kernel   pass 1 of naive_surface_nets (mesh/buffer.rs:77-83)
+//   K1  sample_grids_kernel   pass 1 of naive_surface_nets (mesh/buffer.rs:77-83); also emits the
+//                             sign bit-plane (1 bit per sample, reference layout)
 //   K3  de_batch_kernel       Shape::batch_min_distance_from (shape/mod.rs:89)
-//       (also emits the sign bit-plane: 1 bit per sample, reference layout)
 //   E1  classify_kernel       cell / edge sign classification from the bit-plane, 32 cells per
 //                             thread (buffer.rs:116-147, 299-350)
 //   E2a scan_chunks_kernel    order-preserving prefix over chunk counts
 //   E2b apply_prefix_kernel   per-word prefixes + compacted active-cell list
 //   E3  vertex_kernel         per-active-cell vertex (buffer.rs:150-274)
 //   E4  quad_kernel           per-edge quads, reference emission order (buffer.rs:288-372)
+//   N1  ray_march_kernel      get_focii's sphere tracing (mesh/mod.rs:229-241)
+//   +   iteration_stats_kernel / fma_peak_kernel: measurement aids for bench.py
 //
 // Ordering contract: vertex ids are the rank of the cell among active cells in
 // cube(R) order (x outer, z fastest; util/iter.rs:30-49), quads are emitted
