@@ -208,10 +208,15 @@ def ours_main(args):
     shape = cb.Mandelbulb.classic(MAX_ITERS, BAILOUT, fast=fast)
     sh = shape._ctc_shape()
     volume = workload_spans(args.tiles)
-    # weak scaling: the job is `world` volumes, one per rank (block sharding keeps per-rank work identical)
-    spans = np.ascontiguousarray(np.tile(volume, (world, 1)))
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE volume, spans dealt round-robin over the ranks (total work fixed)
+        spans, shard_mode = volume, "interleave"
+    else:
+        # weak scaling (default): the job is `world` volumes, one per rank (block sharding keeps per-rank work identical)
+        spans, shard_mode = np.ascontiguousarray(np.tile(volume, (world, 1))), "block"
     nspans = spans.shape[0]
-    mine = shard_indices(nspans, world, rank, "block")
+    mine = shard_indices(nspans, world, rank, shard_mode)
     n3 = (RES + 1) ** 3
     total_samples = nspans * n3
 
@@ -234,10 +239,10 @@ def ours_main(args):
         dist.all_reduce(caps)
         caps = caps.cpu().numpy()
         sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
-                                    mode="block", direct=(args.gather == "direct"))
+                                    mode=shard_mode, direct=(args.gather == "direct"))
     else:
         mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
-        sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode="block")
+        sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
 
     local_spans = np.ascontiguousarray(spans[mine])
 
@@ -296,7 +301,7 @@ def ours_main(args):
         capsh[rank, 0], capsh[rank, 1] = pad(nv_loc), pad(ni_loc)
         dist.all_reduce(capsh)
         capsh = capsh.cpu().numpy()
-        hs = HostGatherScheduler(dist, ctx, rank, world, nspans, capsh[:, 0].tolist(), capsh[:, 1].tolist(), mode="block")
+        hs = HostGatherScheduler(dist, ctx, rank, world, nspans, capsh[:, 0].tolist(), capsh[:, 1].tolist(), mode=shard_mode)
         d2h = [0]
 
         def e2e_step_multi():
@@ -415,12 +420,13 @@ def ours_main(args):
             del g512, m1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.tiles == TILES else f"bbox_as_{args.tiles}^3_spans_R64",
                        "spans": int(nspans), "spans_per_gpu": int(len(mine)), "resolution": RES, "power": POWER, "max_iters": MAX_ITERS,
                        "bailout": BAILOUT, "math": "fast" if fast else "exact",
-                       "parallelism": (f"{world} volume(s) of {len(mine)} spans, one per rank (weak scaling), meshes gathered to rank 0"
+                       "parallelism": ((f"{world} volume(s) of {len(mine)} spans, one per rank (weak scaling), meshes gathered to rank 0" if not strong
+                                        else f"one volume of {nspans} spans dealt round-robin over {world} rank(s) (strong scaling), meshes gathered to rank 0")
                                        + ("" if world == 1 else (" by one-sided puts into rank 0's IPC-mapped buffers (copy engines "
                                           "over NVLink, pipelined behind compute)" if args.gather == "peer"
                                           else " by grouped NCCL send/recv"))),
@@ -448,6 +454,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: one volume per rank (weak, default) or one volume sharded over all ranks (strong)")
     ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],
                     help="N>1: copy-engine puts into rank 0's IPC-mapped buffers (default), kernels storing "
                          "straight into them (direct), or NCCL send/recv")
