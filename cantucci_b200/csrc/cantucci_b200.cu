@@ -361,17 +361,25 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     const int variant = shape_variant(shape);
     const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
     // Launch groups.  With the copy pipeline on, the first groups are small (64, 128, 256, ... spans)
-    // so that the device->host / peer copies start almost immediately instead of after a full group.
+    // so that the device->host / peer copies start almost immediately instead of after a full group,
+    // and the last ones shrink again (..., 256, 128, 64) so that little is left to copy once the
+    // compute has finished.
     std::vector<std::pair<size_t, uint32_t>> groups;
     {
+        std::vector<size_t> tail;                       // sizes of the ramp-down groups, last first
+        size_t tail_total = 0;
+        if (pipeline && ctx->group_spans == 0)
+            for (size_t t = 64; t < G && tail_total + t + 64 + 128 + 256 < nspans; t *= 2) { tail.push_back(t); tail_total += t; }
         size_t s0 = 0, ramp = 64;
-        while (s0 < nspans) {
+        const size_t body_end = nspans - tail_total;
+        while (s0 < body_end) {
             size_t cnt = G;
             if (pipeline && ctx->group_spans == 0 && ramp < G) { cnt = ramp; ramp *= 2; }
-            if (cnt > nspans - s0) cnt = nspans - s0;
+            if (cnt > body_end - s0) cnt = body_end - s0;
             groups.emplace_back(s0, (uint32_t)cnt);
             s0 += cnt;
         }
+        for (size_t k = tail.size(); k-- > 0;) { groups.emplace_back(s0, (uint32_t)tail[k]); s0 += tail[k]; }
     }
     const size_t n_groups = groups.size();
     cudaStream_t sA = ctx->stream, sE = ctx->stream;
