@@ -9,10 +9,11 @@ from ._lib import (CantucciError, Context, VERTEX_DTYPE, default_context, lib, L
 from .mesh import MeshBatch, MeshBuffer, Timings, generate_for_boxes, sample_grids
 from .octree import Octree, Span, create_spans, spans_array, startup_tree, tile_volume
 from .shape import Mandelbulb, Shape, Sphere
+from .shape_mesh import ShapeMesh
 
 __all__ = [
     "CantucciError", "Context", "VERTEX_DTYPE", "default_context", "lib", "LIB_PATH",
     "MeshBatch", "MeshBuffer", "Timings", "generate_for_boxes", "sample_grids",
     "Octree", "Span", "create_spans", "spans_array", "startup_tree", "tile_volume",
-    "Mandelbulb", "Shape", "Sphere",
+    "Mandelbulb", "Shape", "Sphere", "ShapeMesh",
 ]

@@ -161,3 +161,57 @@ def test_config5_4096_volume_sharded_subset_and_oracle_sample(oracle, ctx):
     for k, (v, i, _) in zip(pick, meshes):
         got = batch.mesh(int(k))
         assert np.array_equal(got.indices, i) and np.array_equal(got.vertices.view(np.uint32), v.view(np.uint32))
+
+
+# ------------------------------------------------------------------ the caller: ShapeMesh::update ---
+@pytest.mark.gpu
+def test_shape_mesh_update_flies_in_and_matches_oracle(oracle, ctx):
+    """ShapeMesh::update (mesh/mod.rs:82-178) driven by a camera that approaches the bulb: the first
+    frame meshes the 64 startup leaves, later frames split the leaves around the focus points and mesh
+    the new children.  Every Ready leaf must equal the oracle's generate_for_box of its span."""
+    sm = cb.ShapeMesh(cb.Mandelbulb.classic(6, 2.5), ctx, resolution=32)
+    cam = refine.Camera.default_orbit()
+    assert sm.update(cam) == 64                         # frame 1: the startup octree
+    assert sm.update(cam) == 0                          # camera 1.9 away from the surface: nothing splits (threshold 1.2)
+    meshed = []
+    for x in (-2.0, -1.5, -1.2):                        # fly in along the orbit ray
+        cam = refine.Camera(np.array([x, 0.0, 0.0]), np.array([1.0, 0.0, 0.0]))
+        meshed.append(sm.update(cam))
+    assert sum(meshed) > 0 and all(m % 8 == 0 for m in meshed)      # splits create 8 children each
+    ready = sm.ready_meshes()
+    assert len(ready) == 64 + sum(meshed) - sum(meshed) // 8
+    sh = oracle.mandelbulb(8, 6, 2.5)
+    spans = cb.spans_array([s for s, _ in ready])
+    want, _ = oracle.generate_for_boxes_mt(sh, spans, 32)
+    for (span, got), (v, i, _) in zip(ready, want):
+        assert np.array_equal(got.indices, i)
+        assert np.array_equal(got.vertices.view(np.uint32), v.view(np.uint32))
+
+
+# ------------------------------------------------------------------ maximum size the ABI accepts ----
+@pytest.mark.gpu
+def test_resolution_1024_single_span_grid(oracle, ctx):
+    """R = 1024 is the largest resolution (1025^3 = 1.08 G samples, 4.3 GB): pass 1 into a device
+    buffer, spot-checked against the oracle; R = 2048 is refused as an argument error."""
+    import torch
+    from cantucci_b200 import _lib
+    bulb = cb.Mandelbulb.classic(6, 2.5)
+    sh = bulb._ctc_shape()
+    bbox = np.array([[-1.2, -1.2, -1.2, 1.2, 1.2, 1.2]], dtype=np.float32)
+    n = 1025
+    g = torch.empty((n ** 3,), dtype=torch.float32, device="cuda:0")
+    ctx.check(_lib.lib().ctc_sample_grids_device(ctx.handle, C.byref(sh), bbox.ctypes.data, 1, 1024, g.data_ptr()))
+    ctx.synchronize()
+    rng = np.random.default_rng(7)
+    ijk = np.concatenate([rng.integers(0, n, size=(3000, 3)), [[0, 0, 0], [1024, 1024, 1024], [512, 512, 512], [1024, 0, 513]]])
+    flat = (ijk[:, 0] * n + ijk[:, 1]) * n + ijk[:, 2]
+    got = g[torch.from_numpy(flat).to("cuda:0")].cpu().numpy()
+    fr = np.float32(1024)
+    ov = np.float32(np.float32(2.4) / fr)
+    s0 = np.float32(np.float32(-1.2) + (-ov)); e0 = np.float32(np.float32(1.2) + ov)
+    pts = (s0 + np.float32(e0 - s0) * (ijk.astype(np.float32) / fr)).astype(np.float32)
+    want = oracle.batch_min_distance_from(oracle.mandelbulb(8, 6, 2.5), pts)
+    assert np.array_equal(bits(got), bits(want))
+    assert bits(got)[-2] == 0xFFC00000                      # the origin
+    rc = _lib.lib().ctc_sample_grids_device(ctx.handle, C.byref(sh), bbox.ctypes.data, 1, 2048, g.data_ptr())
+    assert rc == _lib.CTC_ERR_INVALID_ARGUMENT
