@@ -239,7 +239,8 @@ def ours_main(args):
         dist.all_reduce(caps)
         caps = caps.cpu().numpy()
         sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
-                                    mode=shard_mode, direct=(args.gather == "direct"))
+                                    mode=shard_mode, direct=(args.gather == "direct"),
+                                    wire_quads=(args.gather == "peer" and not args.wire_u32))
     else:
         mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
         sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
@@ -433,7 +434,7 @@ def ours_main(args):
                        "l2": "per-step working set (4.5 GB of sample grids streamed in 512 MiB launch groups + 0.7 GB of "
                              "mesh per volume) exceeds the 126 MB L2; no explicit flush"},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
-            "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * 4),
+            "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (4 if (args.wire_u32 or args.gather != "peer") else 8 / 6)),
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "other_configs": other,
         }
@@ -454,6 +455,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
+    ap.add_argument("--wire-u32", action="store_true",
+                    help="N>1, --gather peer: ship six u32 indices per quad instead of packed 8-byte quad records")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: one volume per rank (weak, default) or one volume sharded over all ranks (strong)")
     ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],

@@ -67,7 +67,7 @@ EXPORTS = (
     "ctc_mesh_spans", "ctc_mesh_spans_device", "ctc_mesh_result",
     "ctc_iteration_stats", "ctc_fp32_peak_probe",
     "ctc_ray_march", "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
-    "ctc_host_register", "ctc_host_unregister",
+    "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
 )
 
 _lib = None
@@ -138,6 +138,10 @@ def lib() -> C.CDLL:
     L.ctc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.ctc_ipc_close.restype = C.c_int
     L.ctc_ipc_close.argtypes = [vp, vp]
+    L.ctc_ctx_set_index_wire.restype = C.c_int
+    L.ctc_ctx_set_index_wire.argtypes = [vp, C.c_int]
+    L.ctc_expand_quads.restype = C.c_int
+    L.ctc_expand_quads.argtypes = [vp, vp, sz, vp]
     L.ctc_host_register.restype = C.c_int
     L.ctc_host_register.argtypes = [vp, vp, sz]
     L.ctc_host_unregister.restype = C.c_int

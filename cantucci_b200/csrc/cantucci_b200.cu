@@ -62,6 +62,7 @@ struct ctc_ctx {
     uint32_t group_spans = 0;   // 0 = auto
     bool timing = true;
     bool overlap = true;        // ctc_ctx_set_overlap
+    bool wire_quads = false;    // ctc_ctx_set_index_wire: ctc_mesh_spans delivers packed 8-byte quad records
 
     // workspace
     DevBuf geom, grids, sign_bits, m_active, m_ex, m_ey, m_ez, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
@@ -452,10 +453,16 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         }
         {   // pass 3
             PassTimer t(ctx, 2, sE);
-            quad_kernel<<<vblocks, kThreads, 0, sE>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
-                                                              grids, gp.n3, R, lg, gp.words_per_span,
-                                                              ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
-                                                              (unsigned long long)icap);
+            if (pipeline && ctx->wire_quads)
+                quad_kernel<true><<<vblocks, kThreads, 0, sE>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
+                                                                grids, gp.n3, R, lg, gp.words_per_span,
+                                                                ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
+                                                                (unsigned long long)icap);
+            else
+                quad_kernel<false><<<vblocks, kThreads, 0, sE>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
+                                                                 grids, gp.n3, R, lg, gp.words_per_span,
+                                                                 ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
+                                                                 (unsigned long long)icap);
             ctx->launches++;
         }
         if (pipeline) CK(cudaEventRecord(ctx->group_events[gi], sE));
@@ -494,6 +501,8 @@ int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ct
         snprintf(buf, sizeof buf, "lerp factor outside [0,1] in span %u: the reference panics at math.rs:19", st->panic_span);
         return fail(ctx, CTC_ERR_LERP_ASSERT, buf);
     }
+    if (st->wire_overflow)
+        return fail(ctx, CTC_ERR_OVERFLOW, "a span has >= 32768 vertices: packed quad records cannot carry it, use the u32 index wire");
     if (st->overflow) return fail(ctx, CTC_ERR_OVERFLOW, "output capacity too small; required totals reported");
     return CTC_OK;
 }
@@ -573,6 +582,27 @@ int ctc_ctx_set_overlap(ctc_ctx* ctx, int enable) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->overlap = enable != 0;
+    return CTC_OK;
+}
+
+int ctc_ctx_set_index_wire(ctc_ctx* ctx, int packed_quads) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->wire_quads = packed_quads != 0;
+    return CTC_OK;
+}
+
+int ctc_expand_quads(ctc_ctx* ctx, const void* d_records, size_t nquads, uint32_t* d_idx) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nquads == 0) return CTC_OK;
+    if (!d_records || !d_idx || (reinterpret_cast<uintptr_t>(d_idx) & 7u) || (reinterpret_cast<uintptr_t>(d_records) & 7u))
+        return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL or misaligned quad buffers");
+    CK(cudaSetDevice(ctx->device));
+    const unsigned blocks = (unsigned)ctx->num_sms * 8u;
+    expand_quads_kernel<<<blocks, kThreads, 0, ctx->stream>>>(static_cast<const uint2*>(d_records), nquads, d_idx);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return CTC_OK;
 }
 
@@ -704,8 +734,14 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
             done_v = cv;
         }
         if (ci > done_i) {
-            CK(cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
-                               cudaMemcpyDefault, ctx->copy_stream2));
+            if (ctx->wire_quads) {      // packed records: 8 bytes per quad (= per 6 indices), densely at quad offsets
+                const size_t q0 = done_i / 6, q1 = ci / 6;
+                CK(cudaMemcpyAsync(reinterpret_cast<uint2*>(idx) + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2),
+                                   cudaMemcpyDefault, ctx->copy_stream2));
+            } else {
+                CK(cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
+                                   cudaMemcpyDefault, ctx->copy_stream2));
+            }
             done_i = ci;
         }
     }

@@ -43,6 +43,8 @@ struct MeshState {
     unsigned int group_q;
     unsigned int overflow;          // 1 = capacity exceeded somewhere
     unsigned int panic_span;        // min global span index whose lerp factor left [0,1]; 0xFFFFFFFF = none
+    unsigned int wire_overflow;     // 1 = a vertex id did not fit the packed 15-bit quad record
+    unsigned int pad_;
 };
 
 constexpr int kThreads = 256;
@@ -544,9 +546,18 @@ __device__ __forceinline__ uint32_t vertex_id(const uint32_t* __restrict__ activ
     return word_vpre[o] + __popc(active[o] & ((1u << (c & 31u)) - 1u));
 }
 
+// Packed wire record of one quad (8 bytes instead of 24): v0 | v1 << 16, v2 | v3 << 16 | flip << 31 with
+// 15-bit span-local vertex ids; expand_quads_kernel turns it back into the six u32 indices.
+template <bool kPacked>
 __device__ __forceinline__ void store_quad(uint32_t* __restrict__ out_idx, unsigned long long q, unsigned long long icap,
-                                           bool flip, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+                                           bool flip, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3,
+                                           unsigned int* __restrict__ wire_overflow) {
     if (6ull * q + 6ull > icap) return;
+    if (kPacked) {
+        if ((v0 | v1 | v2 | v3) >> 15) { *wire_overflow = 1u; return; }
+        reinterpret_cast<uint2*>(out_idx)[q] = make_uint2(v0 | (v1 << 16), v2 | (v3 << 16) | ((uint32_t)flip << 31));
+        return;
+    }
     uint2* d = reinterpret_cast<uint2*>(out_idx + 6ull * q);
     if (flip) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }   // [v0,v2,v1, v1,v2,v3]
     else      { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }   // [v0,v1,v2, v1,v3,v2]
@@ -556,11 +567,12 @@ __device__ __forceinline__ void store_quad(uint32_t* __restrict__ out_idx, unsig
 // own a sign-changing edge if its cell is active, and there is about one quad per active cell, so
 // the list is a balanced, coalesced work list for the quads as well.  Persistent grid-stride loop
 // (the list length lives on the device).
+template <bool kPacked>
 __global__ void __launch_bounds__(kThreads)
 quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __restrict__ word_qpre,
             const float* __restrict__ grids, size_t grid_stride,
             uint32_t R, uint32_t lg, uint32_t words_per_span, const uint32_t* __restrict__ cell_of, uint32_t cell_cap,
-            const MeshState* __restrict__ st, uint32_t* __restrict__ out_idx, unsigned long long icap) {
+            MeshState* st, uint32_t* __restrict__ out_idx, unsigned long long icap) {
     const uint32_t nv = min(st->group_v, cell_cap);
     const unsigned long long base_q = st->group_base_q;
     const uint32_t n = R + 1u, R2 = R << lg, lg3 = 3 * lg;
@@ -581,17 +593,32 @@ quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __r
         const bool neg = grids[(size_t)span * grid_stride + ((size_t)x * n + y) * n + z] < 0.0f;
         const uint32_t v3 = word_vpre[o] + __popc(m.active[o] & lt);
         if (hx) {   // +x edge, buffer.rs:302-323
-            store_quad(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R - 1u),
-                       vertex_id(m.active, word_vpre, w0, c - R), vertex_id(m.active, word_vpre, w0, c - 1u), v3);
+            store_quad<kPacked>(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R - 1u),
+                                vertex_id(m.active, word_vpre, w0, c - R), vertex_id(m.active, word_vpre, w0, c - 1u), v3,
+                                &st->wire_overflow);
         }
         if (hy) {   // +y edge, buffer.rs:326-347 (winding flipped relative to x/z)
-            store_quad(out_idx, q++, icap, !neg, vertex_id(m.active, word_vpre, w0, c - R2 - 1u),
-                       vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - 1u), v3);
+            store_quad<kPacked>(out_idx, q++, icap, !neg, vertex_id(m.active, word_vpre, w0, c - R2 - 1u),
+                                vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - 1u), v3,
+                                &st->wire_overflow);
         }
         if (hz) {   // +z edge, buffer.rs:350-371
-            store_quad(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R2 - R),
-                       vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - R), v3);
+            store_quad<kPacked>(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R2 - R),
+                                vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - R), v3,
+                                &st->wire_overflow);
         }
+    }
+}
+
+// Widens packed quad records (see store_quad) into the reference's six u32 indices per quad.
+__global__ void __launch_bounds__(kThreads)
+expand_quads_kernel(const uint2* __restrict__ rec, size_t nquads, uint32_t* __restrict__ out_idx) {
+    for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquads; q += (size_t)gridDim.x * kThreads) {
+        const uint2 r = rec[q];
+        const uint32_t v0 = r.x & 0x7FFFu, v1 = (r.x >> 16) & 0x7FFFu, v2 = r.y & 0x7FFFu, v3 = (r.y >> 16) & 0x7FFFu;
+        uint2* d = reinterpret_cast<uint2*>(out_idx + 6 * q);
+        if (r.y >> 31) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }
+        else           { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }
     }
 }
 
@@ -682,6 +709,7 @@ fma_peak_kernel(float* __restrict__ out, uint32_t iters) {
 __global__ void reset_state_kernel(MeshState* st) {
     st->total_v = 0; st->total_q = 0; st->group_base_v = 0; st->group_base_q = 0;
     st->group_v = 0; st->group_q = 0; st->overflow = 0; st->panic_span = 0xFFFFFFFFu;
+    st->wire_overflow = 0; st->pad_ = 0;
 }
 
 }  // namespace ctc

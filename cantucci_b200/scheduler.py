@@ -176,12 +176,17 @@ class PeerGatherScheduler:
     offset tables.  One barrier per step tells rank 0 that every put has landed."""
 
     def __init__(self, dist, torch, ctx: _lib.Context, rank: int, world: int, device, nspans: int,
-                 caps_v: list, caps_i: list, mode: str = "interleave", direct: bool = False):
-        """direct = False: ranks > 0 mesh into local buffers and the copy engines put each launch group's
+                 caps_v: list, caps_i: list, mode: str = "interleave", direct: bool = False,
+                 wire_quads: bool = False):
+        """wire_quads = True (copy-engine mode only): ranks > 0 ship one packed 8-byte record per quad
+        instead of six u32 indices (a third of the index bytes, -31 % of the whole gather) into a wire
+        buffer on rank 0, which widens them into the gathered index buffer after the barrier.
+        direct = False: ranks > 0 mesh into local buffers and the copy engines put each launch group's
         slice into rank 0's region (pipelined).  direct = True: the vertex / quad / scan kernels of
         ranks > 0 store straight into rank 0's mapped region -- compute and gather are one kernel."""
         self.dist, self.torch, self.ctx, self.rank, self.world, self.device = dist, torch, ctx, rank, world, device
         self.nspans, self.mode, self.direct = nspans, mode, direct
+        self.wire_quads = bool(wire_quads) and not direct and world > 1
         self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
         self.n_r = [len(x) for x in self.shards]
         # regions start on 256-byte boundaries (the kernels store 8-byte index pairs)
@@ -192,7 +197,9 @@ class PeerGatherScheduler:
         self.base_t = np.concatenate([[0], np.cumsum([n + 1 for n in self.n_r])]).astype(np.int64)   # table entries
         L = _lib.lib()
         # one table buffer: all v_off tables, then all i_off tables (a single small D2H per step on rank 0)
-        sizes = (int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, 2 * int(self.base_t[-1]) * 8)
+        sizes = [int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, 2 * int(self.base_t[-1]) * 8]
+        if self.wire_quads:
+            sizes.append(int(self.base_i[-1]) // 6 * 8 + 64)      # packed quad records of every rank, at quad offsets
         self.ptrs = [C.c_void_p() for _ in sizes]
         handles = [None]
         if rank == 0:
@@ -243,14 +250,28 @@ class PeerGatherScheduler:
                                               resolution, pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti))
             rc = L.ctc_mesh_result(ctx.handle, None, None, None)
         else:
-            rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
-                                  pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti, None)
+            if self.wire_quads:          # destination: this rank's slot of the wire buffer (8 bytes per quad)
+                pi = self.ptrs[3].value + int(self.base_i[rank]) // 6 * 8
+                L.ctc_ctx_set_index_wire(ctx.handle, 1)
+            try:
+                rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
+                                      pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti, None)
+            finally:
+                if self.wire_quads:
+                    L.ctc_ctx_set_index_wire(ctx.handle, 0)
         ctx.check(rc)
         if world > 1:
             self.dist.barrier()          # every rank's puts have completed (each call synchronised its copy stream)
         if rank != 0:
             return None
         tables = self._views[2].cpu().numpy()      # one small D2H: every rank's offset tables
+        if self.wire_quads:
+            nt = int(self.base_t[-1])
+            for r in range(1, world):    # widen every rank's packed records into the gathered index buffer
+                nq = int(tables[nt + self.base_t[r + 1] - 1]) // 6
+                src = self.ptrs[3].value + int(self.base_i[r]) // 6 * 8
+                dst = self.ptrs[1].value + int(self.base_i[r]) * 4
+                ctx.check(L.ctc_expand_quads(ctx.handle, src, nq, dst))
         return LazyGather(self, tables)
 
 

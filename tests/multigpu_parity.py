@@ -47,20 +47,26 @@ nccl = SpanScheduler(dist, torch, rank, world, device, mesher, cap_v * world, ca
 peer = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world)
 direct = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
                              direct=True)
+packed = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
+                             wire_quads=True)
 host = HostGatherScheduler(dist, ctx, rank, world, len(spans), [cap_v] * world, [cap_i] * world)
 for _ in range(2):
     g1 = nccl.run(sh, spans, R)
     g2 = peer.run(sh, spans, R)
     g3 = direct.run(sh, spans, R)
     g4 = host.run(sh, spans, R)
+    g5 = packed.run(sh, spans, R)
+    torch.cuda.synchronize()
 if rank == 0:
     check(g1, "nccl")
     check(g2, "peer")
     check(g3, "direct")
     check(g4, "host")
+    check(g5, "packed quads")
     print("MULTIGPU_PARITY_OK", world, g2.n_vertices, g2.n_indices, flush=True)
 dist.barrier()
 peer.close()
 direct.close()
 host.close()
+packed.close()
 dist.destroy_process_group()
