@@ -226,11 +226,16 @@ def ours_main(args):
     ctx.check(0)
     nv_req, ni_req = C.c_uint64(0), C.c_uint64(0)
     _lib.lib().ctc_mesh_result(ctx.handle, C.byref(nv_req), C.byref(ni_req), None)
-    del probe
     nv_loc, ni_loc = int(nv_req.value), int(ni_req.value)
+    # the packed quad wire needs every span to stay below 65536 vertices: check it on the sizing run
+    max_span_v = int(probe.v_off[: len(mine) + 1].diff().max()) if len(mine) else 0
+    del probe
     tot = torch.tensor([nv_loc, ni_loc], dtype=torch.int64, device=device)
+    mx = torch.tensor([max_span_v], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    packed_ok = int(mx[0]) < 65536
     nv_tot, ni_tot = int(tot[0]), int(tot[1])
     pad = lambda n: int(n * 1.02) + 1024
     if world > 1 and args.gather in ("peer", "direct"):
@@ -240,7 +245,7 @@ def ours_main(args):
         caps = caps.cpu().numpy()
         sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
                                     mode=shard_mode, direct=(args.gather == "direct"),
-                                    wire_quads=(args.gather == "peer" and not args.wire_u32))
+                                    wire_quads=(args.gather == "peer" and not args.wire_u32 and packed_ok))
     else:
         mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
         sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)

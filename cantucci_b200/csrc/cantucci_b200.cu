@@ -502,7 +502,7 @@ int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ct
         return fail(ctx, CTC_ERR_LERP_ASSERT, buf);
     }
     if (st->wire_overflow)
-        return fail(ctx, CTC_ERR_OVERFLOW, "a span has >= 32768 vertices: packed quad records cannot carry it, use the u32 index wire");
+        return fail(ctx, CTC_ERR_OVERFLOW, "a span has >= 65536 vertices: packed quad records cannot carry it, use the u32 index wire");
     if (st->overflow) return fail(ctx, CTC_ERR_OVERFLOW, "output capacity too small; required totals reported");
     return CTC_OK;
 }

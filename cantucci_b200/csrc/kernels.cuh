@@ -43,7 +43,7 @@ struct MeshState {
     unsigned int group_q;
     unsigned int overflow;          // 1 = capacity exceeded somewhere
     unsigned int panic_span;        // min global span index whose lerp factor left [0,1]; 0xFFFFFFFF = none
-    unsigned int wire_overflow;     // 1 = a vertex id did not fit the packed 15-bit quad record
+    unsigned int wire_overflow;     // 1 = a vertex id did not fit the packed 16-bit quad record
     unsigned int pad_;
 };
 
@@ -546,16 +546,18 @@ __device__ __forceinline__ uint32_t vertex_id(const uint32_t* __restrict__ activ
     return word_vpre[o] + __popc(active[o] & ((1u << (c & 31u)) - 1u));
 }
 
-// Packed wire record of one quad (8 bytes instead of 24): v0 | v1 << 16, v2 | v3 << 16 | flip << 31 with
-// 15-bit span-local vertex ids; expand_quads_kernel turns it back into the six u32 indices.
+// Packed wire record of one quad (8 bytes instead of 24): four 16-bit span-local vertex ids.  The four
+// cells around an edge are always in increasing cube(R) order, so v0 < v1 < v2 < v3, and the winding
+// flag rides on the ORDER of the first two: (v0, v1, v2, v3) = keep, (v1, v0, v2, v3) = flip.
+// expand_quads_kernel turns a record back into the six u32 indices.
 template <bool kPacked>
 __device__ __forceinline__ void store_quad(uint32_t* __restrict__ out_idx, unsigned long long q, unsigned long long icap,
                                            bool flip, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3,
                                            unsigned int* __restrict__ wire_overflow) {
     if (6ull * q + 6ull > icap) return;
     if (kPacked) {
-        if ((v0 | v1 | v2 | v3) >> 15) { *wire_overflow = 1u; return; }
-        reinterpret_cast<uint2*>(out_idx)[q] = make_uint2(v0 | (v1 << 16), v2 | (v3 << 16) | ((uint32_t)flip << 31));
+        if ((v0 | v1 | v2 | v3) >> 16) { *wire_overflow = 1u; return; }
+        reinterpret_cast<uint2*>(out_idx)[q] = make_uint2(flip ? (v1 | (v0 << 16)) : (v0 | (v1 << 16)), v2 | (v3 << 16));
         return;
     }
     uint2* d = reinterpret_cast<uint2*>(out_idx + 6ull * q);
@@ -615,9 +617,11 @@ __global__ void __launch_bounds__(kThreads)
 expand_quads_kernel(const uint2* __restrict__ rec, size_t nquads, uint32_t* __restrict__ out_idx) {
     for (size_t q = (size_t)blockIdx.x * kThreads + threadIdx.x; q < nquads; q += (size_t)gridDim.x * kThreads) {
         const uint2 r = rec[q];
-        const uint32_t v0 = r.x & 0x7FFFu, v1 = (r.x >> 16) & 0x7FFFu, v2 = r.y & 0x7FFFu, v3 = (r.y >> 16) & 0x7FFFu;
+        const uint32_t a = r.x & 0xFFFFu, b = r.x >> 16, v2 = r.y & 0xFFFFu, v3 = r.y >> 16;
+        const bool flip = a > b;
+        const uint32_t v0 = flip ? b : a, v1 = flip ? a : b;
         uint2* d = reinterpret_cast<uint2*>(out_idx + 6 * q);
-        if (r.y >> 31) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }
+        if (flip) { d[0] = make_uint2(v0, v2); d[1] = make_uint2(v1, v1); d[2] = make_uint2(v2, v3); }
         else           { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }
     }
 }

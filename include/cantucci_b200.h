@@ -196,10 +196,10 @@ CTC_API int ctc_ipc_open(ctc_ctx *ctx, const unsigned char handle[64], void **d_
 CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
 
 /* Index wire format of ctc_mesh_spans (the host / peer destination variant only).  0 (default): six
- * u32 indices per quad, the reference's layout.  1: one packed 8-byte record per quad
- * (v0 | v1 << 16, v2 | v3 << 16 | flip << 31; 15-bit span-local vertex ids) written densely at
- * QUAD offsets into `idx` -- a third of the bytes for the multi-GPU gather.  i_off keeps counting
- * indices (6 per quad).  A span with >= 32768 vertices makes the call fail with CTC_ERR_OVERFLOW.
+ * u32 indices per quad, the reference's layout.  1: one packed 8-byte record per quad (four 16-bit
+ * span-local vertex ids; v0 < v1 always holds, so swapping the first two encodes the winding) written
+ * densely at QUAD offsets into `idx` -- a third of the bytes for the multi-GPU gather.  i_off keeps
+ * counting indices (6 per quad).  A span with >= 65536 vertices makes the call fail with CTC_ERR_OVERFLOW.
  * ctc_expand_quads widens nquads records into 6 * nquads u32 indices (device pointers, asynchronous
  * on the context's stream). */
 CTC_API int ctc_ctx_set_index_wire(ctc_ctx *ctx, int packed_quads);
