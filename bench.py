@@ -238,6 +238,9 @@ def ours_main(args):
     packed_ok = int(mx[0]) < 65536
     nv_tot, ni_tot = int(tot[0]), int(tot[1])
     pad = lambda n: int(n * 1.02) + 1024
+    # packed quad records pay off once rank 0's NVLink ingest is the bound (measured: 8 GPUs); below that
+    # the widening pass on rank 0 costs more than the smaller gather saves (4 GPUs: 6.97 vs 6.82 ms)
+    use_packed = (args.gather == "peer" and not args.wire_u32 and packed_ok and (world > 4 or args.wire_packed))
     if world > 1 and args.gather in ("peer", "direct"):
         caps = torch.zeros((world, 2), dtype=torch.int64, device=device)
         caps[rank, 0], caps[rank, 1] = pad(nv_loc), pad(ni_loc)
@@ -245,7 +248,7 @@ def ours_main(args):
         caps = caps.cpu().numpy()
         sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
                                     mode=shard_mode, direct=(args.gather == "direct"),
-                                    wire_quads=(args.gather == "peer" and not args.wire_u32 and packed_ok))
+                                    wire_quads=use_packed)
     else:
         mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
         sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
@@ -439,7 +442,7 @@ def ours_main(args):
                        "l2": "per-step working set (4.5 GB of sample grids streamed in 512 MiB launch groups + 0.7 GB of "
                              "mesh per volume) exceeds the 126 MB L2; no explicit flush"},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
-            "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (4 if (args.wire_u32 or args.gather != "peer") else 8 / 6)),
+            "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (8 / 6 if use_packed else 4)),
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "other_configs": other,
         }
@@ -460,6 +463,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
+    ap.add_argument("--wire-packed", action="store_true", help="N>1: force packed quad records (default only for N > 4)")
     ap.add_argument("--wire-u32", action="store_true",
                     help="N>1, --gather peer: ship six u32 indices per quad instead of packed 8-byte quad records")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
