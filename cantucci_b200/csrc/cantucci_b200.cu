@@ -220,14 +220,16 @@ struct PassTimer {
 template <bool kFast, int kVariant>
 void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint32_t R, uint32_t lg, float* grids,
                    size_t stride, uint32_t nspans, size_t n3, uint32_t* sign_bits, uint32_t sign_stride) {
-    // R >= 32: the R^3 core and the x = R / y = R faces go to the warp-per-256-sample-block path
+    // R >= 32: the R^3 core and the x = R / y = R faces go to the warp-walk path; a warp walks
+    // L = 64 z-samples of its 8 columns when R >= 64 (else 32): per-warp set-up paid once per 512 samples
     const size_t R2 = (size_t)R * R, R3 = R2 * R;
-    const size_t warp_blocks = lg >= 5 ? (R3 + 2 * R2) / 256 : 0;
+    const uint32_t lgw = lg >= 6 ? 1u : 0u;
+    const size_t warp_blocks = lg >= 5 ? (R3 + 2 * R2) / (256u << lgw) : 0;
     const uint32_t core_blocks = (uint32_t)((warp_blocks + 7) / 8);
     const size_t rest = core_blocks ? R2 + 3 * (size_t)R + 1 : n3;
     dim3 grid(core_blocks + (unsigned)((rest + kThreads - 1) / kThreads), nspans);
     sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, 4.0f / (float)R, grids, stride,
-                                                                             sign_bits, sign_stride, core_blocks);
+                                                                             sign_bits, sign_stride, core_blocks, lgw);
     ctx->launches++;
 }
 

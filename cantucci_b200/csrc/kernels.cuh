@@ -103,9 +103,9 @@ __device__ __forceinline__ void decode_sample(uint32_t i, uint32_t R, uint32_t l
 // extraction passes never re-read the 4-byte samples except at active cells.
 // The plane must be zeroed before the launch.
 //
-// Blocks [0, core_blocks), R >= 32: a warp owns a 2x4x32 block of the R^3 core
-// (or a 1x8x32 / 8x1x32 block of the x = R / y = R face) and walks it in 8 steps
-// of one 32-sample brick, so iteration counts inside a warp stay coherent, the
+// Blocks [0, core_blocks), R >= 32: a warp owns a 2x4xL block of the R^3 core
+// (or a 1x8xL / 8x1xL block of the x = R / y = R face; L = 64 for R >= 64, else 32)
+// and walks it in L/4 steps of one 32-sample brick, so iteration counts inside a warp stay coherent, the
 // per-warp set-up (decode, geometry load, x/y position) is paid once per 256
 // samples, and the 8 ballots assemble the 8 row words of the block's sign bits
 // without shared memory.  Remaining blocks: the z = R face, edges and corner
@@ -116,30 +116,31 @@ __global__ void __launch_bounds__(kThreads)
 sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r, float dvz4,
                     float* __restrict__ grids, size_t grid_stride,
                     uint32_t* __restrict__ sign_bits, uint32_t sign_stride /* words per span, 0 = no plane */,
-                    uint32_t core_blocks) {
+                    uint32_t core_blocks, uint32_t lgw /* log2(32-sample words per warp walk): 0 or 1 */) {
     const uint32_t n = R + 1u;
     const SpanGeom g = geom[blockIdx.y];
     float* __restrict__ grid = grids + (size_t)blockIdx.y * grid_stride;
     uint32_t* __restrict__ plane = sign_bits + (size_t)blockIdx.y * sign_stride;
     if (blockIdx.x < core_blocks) {
-        // warp-blocks: [0, R^3/256) core 2x4x32; then R^2/256 blocks 1x8x32 of the x = R face; then
-        // R^2/256 blocks 8x1x32 of the y = R face.  All three walk 32 z-samples in 8 brick steps.
+        // warp-blocks of L = 32 << lgw z-samples: [0, R^3/(8L)) core 2x4xL; then R^2/(8L) blocks 1x8xL of
+        // the x = R face; then R^2/(8L) blocks 8x1xL of the y = R face.  Each is walked in L/4 brick steps.
         const uint32_t lane = threadIdx.x & 31u;
         const uint32_t wb = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-        const uint32_t n_core = 1u << (3 * lg - 8), n_face = 1u << (2 * lg - 8);
+        const uint32_t lgL = 5u + lgw;
+        const uint32_t n_core = 1u << (3 * lg - 3 - lgL), n_face = 1u << (2 * lg - 3 - lgL);
         if (wb >= n_core + 2u * n_face) return;
         uint32_t x, y, zb;
         if (wb < n_core) {
-            zb = wb & ((R >> 5) - 1u);
-            x = ((wb >> (2 * lg - 7)) << 1) | (lane >> 4);
-            y = (((wb >> (lg - 5)) & ((R >> 2) - 1u)) << 2) | ((lane >> 2) & 3u);
+            zb = wb & ((R >> lgL) - 1u);
+            x = ((wb >> (2 * lg - lgL - 2)) << 1) | (lane >> 4);
+            y = (((wb >> (lg - lgL)) & ((R >> 2) - 1u)) << 2) | ((lane >> 2) & 3u);
         } else {
             const uint32_t f = wb - n_core, ff = f & (n_face - 1u);
-            zb = ff & ((R >> 5) - 1u);
-            const uint32_t t = ((ff >> (lg - 5)) << 3) | (lane >> 2);
+            zb = ff & ((R >> lgL) - 1u);
+            const uint32_t t = ((ff >> (lg - lgL)) << 3) | (lane >> 2);
             if (f < n_face) { x = R; y = t; } else { x = t; y = R; }
         }
-        const uint32_t z = (zb << 5) | (lane & 3u);
+        const uint32_t z = (zb << lgL) | (lane & 3u);
         // v = (x,y,z) as f32 / R  (exact: R is a power of two);  p = start + across * v  (buffer.rs:79-80)
         const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
         const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
@@ -148,19 +149,31 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         uint32_t row_shift = (lane >> 2) << 2;          // this lane's row (xl,yl) nibble in a brick ballot
         asm volatile("" : "+r"(row_shift));             // keep it in a register (no S2R re-read per step)
         const float gs2 = g.s[2], ga2 = g.across[2];
-        uint32_t word = 0;
+        const uint32_t j_row = (x * n + y) * n + (zb << lgL);     // plane bit of this lane's row at the block's first z
+        const bool writer = sign_stride != 0u && (lane & 3u) == 0u;
         // the fast DE's on-axis special case is tested once per warp, not once per sample
         const bool any_axis = kFast && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
+        // 8 steps fill one 32-bit row word of the sign plane, which is then OR-ed in (two atomics)
 #define CTC_K1_STEPS(DE_EXPR)                                                                      \
         _Pragma("unroll 1")                                                                        \
-        for (int j = 0; j < 8; ++j) {                                                              \
-            const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));                                   \
-            const float d = DE_EXPR;                                                               \
-            *out = d;                                                                              \
-            out += 4;                                                                              \
-            const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);               \
-            word = __funnelshift_r(word, b >> row_shift, 4);   /* nibble j -> bits [4j, 4j+4) */   \
-            vz = __fadd_rn(vz, dvz4);                                                              \
+        for (uint32_t h = 0; h < (1u << lgw); ++h) {                                               \
+            uint32_t word = 0;                                                                     \
+            _Pragma("unroll 1")                                                                    \
+            for (int j = 0; j < 8; ++j) {                                                          \
+                const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));                               \
+                const float d = DE_EXPR;                                                           \
+                *out = d;                                                                          \
+                out += 4;                                                                          \
+                const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);           \
+                word = __funnelshift_r(word, b >> row_shift, 4);   /* nibble j -> bits [4j, 4j+4) */ \
+                vz = __fadd_rn(vz, dvz4);                                                          \
+            }                                                                                      \
+            if (writer && word != 0u) {                                                            \
+                const uint32_t j0 = j_row + (h << 5);                                              \
+                const uint32_t sft = j0 & 31u;                                                     \
+                atomicOr(&plane[j0 >> 5], word << sft);                                            \
+                if (sft) atomicOr(&plane[(j0 >> 5) + 1u], word >> (32u - sft));                    \
+            }                                                                                      \
         }
         if (any_axis) {
             CTC_K1_STEPS((shape_de<kFast, kVariant, true>(sh, px, py, pz)))
@@ -175,12 +188,6 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
             CTC_K1_STEPS((shape_de<kFast, kVariant, false>(sh, px, py, pz)))
         }
 #undef CTC_K1_STEPS
-        if (sign_stride != 0u && (lane & 3u) == 0u && word != 0u) {
-            const uint32_t j0 = (x * n + y) * n + (zb << 5);
-            const uint32_t sft = j0 & 31u;
-            atomicOr(&plane[j0 >> 5], word << sft);
-            if (sft) atomicOr(&plane[(j0 >> 5) + 1u], word >> (32u - sft));
-        }
         return;
     }
     // one thread per remaining sample: everything when R < 32, else the z = R face, the three edges
