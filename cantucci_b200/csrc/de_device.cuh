@@ -196,6 +196,69 @@ __device__ __forceinline__ float mandelbulb_de_exact(const ShapeDev& s, float px
     return canonical_x86_nan(M::div(M::mul(0.5f, ln_r), dr));
 }
 
+// EXACT power-8 DE along a lattice COLUMN (K1 walks z with (px, py) fixed): every sub-expression of
+// the FIRST iteration that depends on x and y only is computed once per column.  Pure common-
+// subexpression hoisting: each value is produced by the same IEEE operation on the same operands as
+// in rotate_p8_exact / mandelbulb_de_exact, so the result is bit-identical.
+struct ColumnExactP8 {
+    float w2, w4, w6, w8, sqrt_w2, poly_x, poly_y;
+};
+
+__device__ __forceinline__ ColumnExactP8 column_exact_p8(float x, float y) {
+    using M = MathExact;
+    ColumnExactP8 c;
+    const float x2 = M::mul(x, x), x4 = M::mul(x2, x2), x6 = M::mul(x4, x2), x8 = M::mul(x4, x4);
+    const float y2 = M::mul(y, y), y4 = M::mul(y2, y2), y6 = M::mul(y4, y2), y8 = M::mul(y4, y4);
+    c.w2 = M::add(x2, y2); c.w4 = M::mul(c.w2, c.w2); c.w6 = M::mul(c.w2, c.w4); c.w8 = M::mul(c.w4, c.w4);
+    c.sqrt_w2 = M::sqrt(c.w2);
+    float px = M::sub(x8, M::mul(M::mul(28.0f, x6), y2));
+    px = M::add(px, M::mul(M::mul(70.0f, x4), y4));
+    px = M::sub(px, M::mul(M::mul(28.0f, x2), y6));
+    c.poly_x = M::sub(px, y8);
+    float py = M::sub(x6, M::mul(M::mul(7.0f, x4), y2));
+    py = M::add(py, M::mul(M::mul(7.0f, x2), y4));
+    c.poly_y = M::sub(py, y6);
+    return c;
+}
+
+// Caller guarantees (px, py) != (+-0, +-0) (the z-axis special case is handled per warp in K1).
+__device__ __forceinline__ float mandelbulb_de_exact_p8_column(const ShapeDev& s, float px, float py, float pz,
+                                                               const ColumnExactP8& c) {
+    using M = MathExact;
+    float dr = 1.0f;
+    const float z2 = M::mul(pz, pz);
+    float r = M::sqrt(M::add(c.w2, z2));                     // sqrt((x*x + y*y) + z*z)
+    if (!(r > s.bailout)) {
+        // dr = r.powi(7) * 8 * 1.0 + 1.0   (the multiplication by dr = 1.0 is exact)
+        dr = M::add(M::mul(powi<M>(r, 7u), 8.0f), 1.0f);
+        const float z4 = M::mul(z2, z2), z6 = M::mul(z4, z2), z8 = M::mul(z4, z4);
+        float t = M::sub(z8, M::mul(M::mul(28.0f, z6), c.w2));
+        t = M::add(t, M::mul(M::mul(70.0f, z4), c.w4));
+        t = M::sub(t, M::mul(M::mul(28.0f, z2), c.w6));
+        const float a = M::add(1.0f, M::div(t, c.w8));
+        const float ox = M::mul(a, c.poly_x);
+        const float oy = M::mul(M::mul(M::mul(M::mul(8.0f, a), px), py), c.poly_y);
+        const float pz4 = M::add(M::sub(z4, M::mul(M::mul(6.0f, z2), c.w2)), c.w4);
+        const float oz = M::mul(M::mul(M::mul(M::mul(8.0f, pz), c.sqrt_w2), M::sub(z2, c.w2)), pz4);
+        float zx = M::add(ox, px), zy = M::add(oy, py), zz = M::add(oz, pz);
+        for (uint32_t it = 1; it < s.max_iters; ++it) {
+            r = M::sqrt(M::add(M::add(M::mul(zx, zx), M::mul(zy, zy)), M::mul(zz, zz)));
+            if (r > s.bailout) break;
+            dr = M::add(M::mul(M::mul(powi<M>(r, 7u), 8.0f), dr), 1.0f);
+            float nx, ny, nz;
+            if (zx == 0.0f && zy == 0.0f) {
+                nx = 0.0f; ny = 0.0f;
+                nz = rotate_on_z_axis_exact(8u, zz, r);
+            } else {
+                rotate_p8_exact(zx, zy, zz, nx, ny, nz);
+            }
+            zx = M::add(nx, px); zy = M::add(ny, py); zz = M::add(nz, pz);
+        }
+    }
+    const float ln_r = M::mul(M::log(r), r);
+    return canonical_x86_nan(M::div(M::mul(0.5f, ln_r), dr));
+}
+
 // ---------------------------------------------------------------------------
 // FAST: same recurrence, FMA-contracted and re-associated
 // ---------------------------------------------------------------------------

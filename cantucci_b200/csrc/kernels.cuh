@@ -151,8 +151,8 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         const float gs2 = g.s[2], ga2 = g.across[2];
         const uint32_t j_row = (x * n + y) * n + (zb << lgL);     // plane bit of this lane's row at the block's first z
         const bool writer = sign_stride != 0u && (lane & 3u) == 0u;
-        // the fast DE's on-axis special case is tested once per warp, not once per sample
-        const bool any_axis = kFast && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
+        // the on-axis special case of the column paths is tested once per warp, not once per sample
+        const bool any_axis = (kFast || kVariant == kVarP8) && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
         // 8 steps fill one 32-bit row word of the sign plane, which is then OR-ed in (two atomics)
 #define CTC_K1_STEPS(DE_EXPR)                                                                      \
         _Pragma("unroll 1")                                                                        \
@@ -184,6 +184,10 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
             p8_azimuth(px, py, w2c, iw, c8, s8h);
             const float wc = w2c * iw;
             CTC_K1_STEPS((mandelbulb_de_fast_p8_column(sh, px, py, pz, w2c, wc, c8, s8h)))
+        } else if (!kFast && kVariant == kVarP8) {
+            // exact arithmetic: hoist the x/y-only sub-expressions of the first iteration (bit-identical CSE)
+            const ColumnExactP8 col = column_exact_p8(px, py);
+            CTC_K1_STEPS((mandelbulb_de_exact_p8_column(sh, px, py, pz, col)))
         } else {
             CTC_K1_STEPS((shape_de<kFast, kVariant, false>(sh, px, py, pz)))
         }
