@@ -53,11 +53,11 @@ constexpr uint32_t kMaxChunkWords = 256;  // one word per thread in E2b
 // ---------------------------------------------------------------------------
 // sample index -> lattice coordinates
 // ---------------------------------------------------------------------------
-// Samples of one span are enumerated so that (a) every warp is full and (b) a
-// warp covers a compact 2x4x4 brick of the R^3 core (iteration counts are
-// spatially coherent; bricks cut divergence loss from ~13% to ~4% versus
-// 32-long z rows).  The (R+1)^3 lattice = R^3 core + three R^2 faces + three
-// R-long edges + 1 corner; every piece has power-of-two extent, so decoding is
+// One-thread-per-sample enumeration (used for R < 32 and by the iteration-statistics kernel; K1's
+// main path for R >= 32 walks lattice columns instead, see sample_grids_kernel).  Every warp is full
+// and covers a compact 2x4x4 brick of the R^3 core: iteration counts are spatially coherent, bricks
+// lose ~1-4 % to divergence where 32-long z rows lose ~13 %.  The (R+1)^3 lattice = R^3 core + three
+// R^2 faces + three R-long edges + 1 corner; every piece has power-of-two extent, so decoding is
 // shifts and masks only.
 __device__ __forceinline__ void decode_sample(uint32_t i, uint32_t R, uint32_t lg,
                                               uint32_t& x, uint32_t& y, uint32_t& z) {
@@ -455,8 +455,6 @@ apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_counts, const uint2
 // E3: vertices.  Persistent grid-stride loop over the group's compacted active
 // cells (the count lives on the device, no host sync).  One thread per vertex.
 // ---------------------------------------------------------------------------
-struct VertexOut { float px, py, pz, nx, ny, nz, d; };
-
 template <bool kFast, int kVariant>
 __global__ void __launch_bounds__(kThreads, 5)
 vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __restrict__ grids, size_t grid_stride,
