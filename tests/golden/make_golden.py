@@ -43,6 +43,14 @@ def main():
     np.savez_compressed(os.path.join(HERE, "small_meshes.npz"),
                         bulb_v=v.view(np.uint32).reshape(-1, 7), bulb_i=i,
                         sphere_v=sv.view(np.uint32).reshape(-1, 7), sphere_i=si)
+    # config 3: the leaf set of the refinement mirror (host logic), driven by the oracle's DE
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_configs import _OracleBulb
+    from cantucci_b200 import refine
+    spans3, cam = refine.config3_spans(_OracleBulb.classic(6, 2.5), 6)
+    json.dump({"n_leaves": int(len(spans3)), "spans_sha256": hashlib.sha256(spans3.tobytes()).hexdigest(),
+               "camera_position": [float(c) for c in cam.position]},
+              open(os.path.join(HERE, "config3_leaves.json"), "w"), indent=1)
     print("golden fixtures written")
 
 

@@ -34,6 +34,9 @@ def test_config3_refinement_host_logic():
     # leaves tile the bounding box exactly: volumes add up
     vol = np.prod((spans[:, 3:] - spans[:, :3]).astype(np.float64), axis=1).sum()
     assert abs(vol - 2.4 ** 3) < 1e-4
+    import hashlib, json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "config3_leaves.json")))
+    assert gold["n_leaves"] == len(spans) and gold["spans_sha256"] == hashlib.sha256(spans.tobytes()).hexdigest()
 
 
 # ------------------------------------------------------------------ config 3 (GPU parity) ----------

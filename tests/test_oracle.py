@@ -76,6 +76,31 @@ def test_polynomial_and_trig_power8_are_not_the_same_map(oracle):
     assert np.array_equal(bits(oracle.rotate(8, p, "dispatch")), bits(oracle.rotate(8, p, "p8_scalar")))
 
 
+def test_generic_de_agrees_with_the_glsl_statement_of_the_math(oracle):
+    """src/shape/mandelbulb.frag:1-39 states the generic-power DE a second time (GLSL, no z-axis special
+    case).  Evaluated here in float64 it must agree with the oracle's f32 generic path to f32 accuracy on
+    samples that escape early (later escapes amplify rounding)."""
+    def glsl_de(p, power, max_iters, bailout):
+        z = np.array(p, dtype=np.float64); dr = 1.0; r = 0.0
+        for _ in range(max_iters):
+            r = np.linalg.norm(z)
+            if r > bailout:
+                break
+            theta = np.arccos(z[2] / r); phi = np.arctan2(z[1], z[0])
+            dr = r ** (power - 1.0) * power * dr + 1.0
+            zr = r ** power
+            theta *= power; phi *= power
+            z = zr * np.array([np.sin(theta) * np.cos(phi), np.sin(phi) * np.sin(theta), np.cos(theta)]) + p
+        return 0.5 * np.log(r) * r / dr
+    pts = rand_points(400, 9, 0.9, 1.3)         # outside the bulb: escape within a few iterations
+    for power in (2, 4, 16):
+        sh = oracle.mandelbulb(power, 12, 2.5)
+        for p in pts:
+            d, info = oracle.min_distance_from_info(sh, p)
+            if info.bailed and info.iters <= 2 and info.min_margin > 1e-3:
+                assert abs(d - glsl_de(p.astype(np.float64), power, 12, 2.5)) <= 2e-5 * abs(d) + 1e-7, (power, p)
+
+
 def test_sphere_de_is_analytic(oracle):
     sh = oracle.sphere((0.1, -0.2, 0.3), 0.75)
     pts = rand_points(1000, 3)
