@@ -483,6 +483,10 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
         const float p0y = M::add(g.s[1], M::mul((float)y, g.step[1]));
         const float p0z = M::add(g.s[2], M::mul((float)z, g.step[2]));
 
+        // corner coordinates p0 + corner_offsets[i] (buffer.rs:102-111, 242): the offset is 0.0 or step per axis
+        const float cx0 = M::add(p0x, 0.0f), cx1 = M::add(p0x, g.step[0]);
+        const float cy0 = M::add(p0y, 0.0f), cy1 = M::add(p0y, g.step[1]);
+        const float cz0 = M::add(p0z, 0.0f), cz1 = M::add(p0z, g.step[2]);
         // 12 edges (buffer.rs:155-176): from/to corner ids packed 4 bits each
         // x edges (0,4)(1,5)(2,6)(3,7); y edges (0,2)(1,3)(4,6)(5,7); z edges (0,1)(2,3)(4,5)(6,7)
         const unsigned long long kFrom = 0x642054103210ull, kTo = 0x753176327654ull;
@@ -502,9 +506,9 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
             if (!(w >= 0.0f && w <= 1.0f)) bad = true;                                     // math.rs:19
             const float om = M::sub(1.0f, w);
             // lerp(p0 + off[from], p0 + off[to], w) = a*(1-w) + b*w   (math.rs:45-48)
-            const float ax = M::add(p0x, (from & 4) ? g.step[0] : 0.0f), bx = M::add(p0x, (to & 4) ? g.step[0] : 0.0f);
-            const float ay = M::add(p0y, (from & 2) ? g.step[1] : 0.0f), by = M::add(p0y, (to & 2) ? g.step[1] : 0.0f);
-            const float az = M::add(p0z, (from & 1) ? g.step[2] : 0.0f), bz = M::add(p0z, (to & 1) ? g.step[2] : 0.0f);
+            const float ax = (from & 4) ? cx1 : cx0, bx = (to & 4) ? cx1 : cx0;
+            const float ay = (from & 2) ? cy1 : cy0, by = (to & 2) ? cy1 : cy0;
+            const float az = (from & 1) ? cz1 : cz0, bz = (to & 1) ? cz1 : cz0;
             sx_ = M::add(sx_, M::add(M::mul(ax, om), M::mul(bx, w)));
             sy_ = M::add(sy_, M::add(M::mul(ay, om), M::mul(by, w)));
             sz_ = M::add(sz_, M::add(M::mul(az, om), M::mul(bz, w)));
@@ -520,7 +524,7 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
         // dist_p and the un-normalised central differences (buffer.rs:254-265).
         // unit_x() * d = (1*d, 0*d, 0*d): the zero products keep their sign.
         float de[7];
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int axis = (k - 1) >> 1;                 // k=0: none
             const float sg = (k & 1) ? 1.0f : -1.0f;       // odd k: +delta, even k: -delta
