@@ -103,6 +103,18 @@ int fail_cuda(ctc_ctx* c, cudaError_t e, const char* where) {
 }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail_cuda(ctx, _e, #call); } while (0)
 
+// No C++ exception may cross the C ABI (std::vector / std::string can throw bad_alloc).
+template <class F>
+int guarded(ctc_ctx* ctx, F&& body) {
+    try {
+        return body();
+    } catch (const std::exception& e) {
+        return fail(ctx, CTC_ERR_CUDA, e.what());
+    } catch (...) {
+        return fail(ctx, CTC_ERR_CUDA, "unknown C++ exception");
+    }
+}
+
 // The reference's asserts on the shape (mandelbulb.rs:20) and what this build supports.
 int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
     if (!s) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "shape is NULL");
@@ -679,20 +691,18 @@ int ctc_mesh_spans_device(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* 
                           uint64_t* d_i_off) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return mesh_spans_impl(ctx, shape, spans, nspans, resolution, d_v, vcap, d_idx, icap, d_v_off, d_i_off);
+    return guarded(ctx, [&] { return mesh_spans_impl(ctx, shape, spans, nspans, resolution, d_v, vcap, d_idx, icap, d_v_off, d_i_off); });
 }
 
 int ctc_mesh_result(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc_timings* timings) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return mesh_result_impl(ctx, n_vertices, n_indices, timings);
+    return guarded(ctx, [&] { return mesh_result_impl(ctx, n_vertices, n_indices, timings); });
 }
 
-int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
-                   ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
-                   ctc_timings* timings) {
-    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+static int mesh_spans_host(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                           ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
+                           ctc_timings* timings) {
     if (!v_off || !i_off) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "offset tables are NULL");
     if ((vcap && !v) || (icap && !idx)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL output buffer with non-zero capacity");
     CK(cudaSetDevice(ctx->device));
@@ -756,6 +766,14 @@ int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
         memcpy(i_off, static_cast<char*>(ctx->h_tables.p) + tbytes, tbytes);
     }
     return status;
+}
+
+int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                   ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
+                   ctc_timings* timings) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return guarded(ctx, [&] { return mesh_spans_host(ctx, shape, spans, nspans, resolution, v, vcap, idx, icap, v_off, i_off, timings); });
 }
 
 int ctc_ray_march(ctc_ctx* ctx, const ctc_shape* shape, const float* origin, const float* dir, size_t n,
