@@ -1,6 +1,6 @@
 """Relative error of the tolerance modes against the oracle, bucketed by completed iterations."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import cantucci_b200 as cb
 from oracle import oracle as O
