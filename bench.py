@@ -305,7 +305,18 @@ def ours_main(args):
     # (ctc_mesh_spans) into ITS region of one shared, page-locked host segment, i.e. the device->host
     # copies of the N ranks run in parallel over N PCIe links; rank 0 reads all offset tables there.
     e2e_multi = None
+    shm_ok = True
     if world > 1:
+        # the shared segment lives in /dev/shm: make sure it fits before every rank commits to it
+        import shutil
+        need = int((nv_tot * 28 + ni_tot * 4) * 1.1) + (64 << 20)
+        flag = torch.tensor([1 if (rank != 0 or shutil.disk_usage("/dev/shm").free > need) else 0],
+                            dtype=torch.int64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        shm_ok = bool(int(flag[0]))
+        if not shm_ok:
+            e2e_multi = {"value": None, "unit": UNIT, "note": f"/dev/shm cannot hold the {need >> 20} MiB shared host segment"}
+    if world > 1 and shm_ok:
         capsh = torch.zeros((world, 2), dtype=torch.int64, device=device)
         capsh[rank, 0], capsh[rank, 1] = pad(nv_loc), pad(ni_loc)
         dist.all_reduce(capsh)
