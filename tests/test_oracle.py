@@ -169,6 +169,33 @@ def test_mesher_matches_numpy_restatement_on_a_sphere_and_is_analytic(oracle):
     assert np.all(np.sum(nrm * cen, axis=1) > 0)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_mesher_matches_numpy_restatement_on_random_shapes_and_spans(oracle, seed):
+    """Randomised cross-check of the two independent restatements: random anisotropic spans, Sphere
+    with random centre/radius or Mandelbulb with P in {2, 4, 8}, R in {4, 8}."""
+    rng = np.random.default_rng(100 + seed)
+    R = int(rng.choice([4, 8]))
+    start = rng.uniform(-1.1, 0.2, 3).astype(np.float32)
+    end = (start + rng.uniform(0.3, 0.9, 3)).astype(np.float32)
+    if seed % 2:
+        c = rng.uniform(-0.3, 0.3, 3).astype(np.float32); rad = float(np.float32(rng.uniform(0.5, 0.9)))
+        sh, de = oracle.sphere(tuple(c), rad), (lambda p: NP.sphere_de(p, c, rad))
+    else:
+        P = int(rng.choice([2, 4, 8])); iters = int(rng.integers(3, 8))
+        sh, de = oracle.mandelbulb(P, iters, 2.5), (lambda p: NP.mandelbulb_de(p, P, iters, 2.5)[0])
+    try:
+        V, I, dists = NP.naive_surface_nets(de, start, end, R)
+    except AssertionError:          # the numpy restatement hit the lerp assert: the oracle must report the panic too
+        with pytest.raises(AssertionError):
+            oracle.generate_for_box(sh, oracle.make_span(start, end), R)
+        return
+    v, idx, _ = oracle.generate_for_box(sh, oracle.make_span(start, end), R)
+    assert np.array_equal(bits(oracle.sample_grid(sh, oracle.make_span(start, end), R)), bits(dists.ravel()))
+    assert np.array_equal(idx, I) and len(v) == len(V)
+    got = np.concatenate([v["position"], v["normal"], v["distance_from_surface"][:, None]], axis=1)
+    assert np.array_equal(bits(got), bits(V))
+
+
 def test_argument_asserts(oracle):
     sh = oracle.mandelbulb(8, 6, 2.5)
     with pytest.raises(AssertionError):
