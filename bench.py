@@ -151,6 +151,112 @@ def run_cpu(spans: np.ndarray, threads: int | None = None):
     return {"secs": secs, "samples": samples, "spans": spans.shape[0], "threads": threads, "vertices": nv, "quads": nq}
 
 
+# ---------------------------------------------------------------------------
+# parity gate (last bullet): runs with every measurement, outside the timed region
+# ---------------------------------------------------------------------------
+def oracle_volume(spans: np.ndarray, threads: int | None = None, signs: bool = True):
+    """The CPU oracle over `spans`: flat meshes + sign planes, and the pool's wall time (which is also the
+    cpu_baseline / reference-arm measurement: one span per task on all host threads, mesh/mod.rs:61-62,141)."""
+    from oracle import oracle as O
+    sh = O.mandelbulb(POWER, MAX_ITERS, BAILOUT)
+    threads = threads or O.hardware_threads()
+    v, i, v_off, i_off, planes, panicked, secs = O.generate_for_boxes_flat_mt(sh, spans, RES, threads, signs=signs)
+    return {"v": v, "i": i, "v_off": v_off, "i_off": i_off, "planes": planes, "panicked": panicked, "secs": secs,
+            "threads": threads, "spans": int(spans.shape[0]), "samples": int(spans.shape[0]) * (RES + 1) ** 3}
+
+
+def _popcount_xor(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Per-row popcount of a ^ b for [n, words] u32 arrays."""
+    x = np.bitwise_xor(a, b)
+    if not x.any():
+        return np.zeros(x.shape[0], dtype=np.int64)
+    rows = np.nonzero(x.any(axis=1))[0]
+    out = np.zeros(x.shape[0], dtype=np.int64)
+    out[rows] = np.unpackbits(x[rows].view(np.uint8), axis=1).sum(axis=1)
+    return out
+
+
+# Stated tolerances of the benched (fast) math mode against the reference's CPU mesher (DESIGN.md section 3):
+# positions in units of the span's cell edge, normals as the Euclidean distance of the unit vectors,
+# distance_from_surface in units of the cell edge.  Exact mode: everything is bit-identical (tolerance 0).
+PARITY_TOL = {"position_cells_max": 2e-2, "position_cells_p99": 1e-4, "normal_max": 0.5, "normal_p99": 2e-3,
+              "distance_cells_max": 2e-2, "distance_cells_p99": 1e-4}
+
+
+def parity_gate(gpu_v, gpu_i, gpu_v_off, gpu_i_off, gpu_planes, ora, spans: np.ndarray, exact: bool):
+    """Compares the CUDA path's result (host arrays, as delivered through the C ABI) with the oracle's on
+    the same spans: sign field, offset tables, index buffers, vertex records.  Returns the `parity` dict."""
+    import hashlib
+    ns = spans.shape[0]
+    n3 = (RES + 1) ** 3
+    flips = _popcount_xor(gpu_planes, ora["planes"])
+    sign_mismatches = int(flips.sum())
+    bad_spans = np.nonzero(flips)[0]
+    gv_off, gi_off = gpu_v_off.astype(np.int64), gpu_i_off.astype(np.int64)
+    same_counts = (np.diff(gv_off) == np.diff(ora["v_off"])) & (np.diff(gi_off) == np.diff(ora["i_off"]))
+    out = {"samples": ns * n3, "sign_mismatches": sign_mismatches, "spans_with_sign_mismatch": int(bad_spans.size),
+           "spans": ns, "spans_reference_panicked": len(ora["panicked"]),
+           "vertices": int(gv_off[-1]), "vertices_reference": int(ora["v_off"][-1]),
+           "indices": int(gi_off[-1]), "indices_reference": int(ora["i_off"][-1]),
+           "spans_with_different_counts": int((~same_counts).sum())}
+    whole = bool(same_counts.all()) and sign_mismatches == 0
+    if whole:
+        gi, oi = gpu_i[: gi_off[-1]], ora["i"]
+        out["index_buffers_identical"] = bool(np.array_equal(gi, oi))
+        out["indices_sha256"] = hashlib.sha256(np.ascontiguousarray(gi).tobytes()).hexdigest()
+        out["indices_sha256_reference"] = hashlib.sha256(np.ascontiguousarray(oi).tobytes()).hexdigest()
+        sel_v = slice(0, int(gv_off[-1]))
+        gvv, ovv = gpu_v[sel_v], ora["v"]
+        cell = np.repeat(((spans[:, 3] - spans[:, 0]) * (1.0 + 2.0 / RES) / RES).astype(np.float64), np.diff(gv_off))
+    else:
+        # compare span by span where the sign field (hence the topology) agrees
+        ok = np.nonzero(same_counts & (flips == 0))[0]
+        ident = sum(bool(np.array_equal(gpu_i[gi_off[k]: gi_off[k + 1]], ora["i"][ora["i_off"][k]: ora["i_off"][k + 1]])) for k in ok)
+        out["index_buffers_identical"] = False
+        out["spans_with_matching_signs"] = int(ok.size)
+        out["spans_with_matching_signs_and_identical_indices"] = int(ident)
+        gsel = np.concatenate([np.arange(gv_off[k], gv_off[k + 1]) for k in ok]) if ok.size else np.zeros(0, np.int64)
+        osel = np.concatenate([np.arange(ora["v_off"][k], ora["v_off"][k + 1]) for k in ok]) if ok.size else np.zeros(0, np.int64)
+        gvv, ovv = gpu_v[gsel], ora["v"][osel]
+        cell = np.repeat(((spans[ok, 3] - spans[ok, 0]) * (1.0 + 2.0 / RES) / RES).astype(np.float64),
+                         (gv_off[ok + 1] - gv_off[ok]))
+    out["vertices_compared"] = int(len(gvv))
+    if len(gvv):
+        out["vertex_records_bit_identical"] = bool(np.array_equal(gvv.view(np.uint32), ovv.view(np.uint32)))
+
+        def stats(err):
+            err = err[np.isfinite(err)]
+            return (float(err.max()), float(np.quantile(err, 0.99))) if err.size else (0.0, 0.0)
+        dp = np.abs(gvv["position"].astype(np.float64) - ovv["position"]).max(axis=1) / cell
+        gn, on = gvv["normal"].astype(np.float64), ovv["normal"].astype(np.float64)
+        both_nan = np.isnan(gn).any(axis=1) & np.isnan(on).any(axis=1)
+        one_nan = np.isnan(gn).any(axis=1) ^ np.isnan(on).any(axis=1)
+        dn = np.linalg.norm(gn - on, axis=1)
+        dd = np.abs(gvv["distance_from_surface"].astype(np.float64) - ovv["distance_from_surface"]) / cell
+        out["position_err_cells_max"], out["position_err_cells_p99"] = stats(dp)
+        out["normal_err_max"], out["normal_err_p99"] = stats(dn[~both_nan & ~one_nan])
+        out["distance_err_cells_max"], out["distance_err_cells_p99"] = stats(dd)
+        out["normals_nan_in_both"], out["normals_nan_in_one"] = int(both_nan.sum()), int(one_nan.sum())
+    tol = {k: 0.0 for k in PARITY_TOL} if exact else PARITY_TOL
+    out["tolerances"] = tol
+    out["ok"] = bool(
+        sign_mismatches == 0 and out["spans_with_different_counts"] == 0 and out["index_buffers_identical"]
+        and (not len(gvv) or (
+            out["position_err_cells_max"] <= tol["position_cells_max"] and out["position_err_cells_p99"] <= tol["position_cells_p99"]
+            and out["normal_err_max"] <= tol["normal_max"] and out["normal_err_p99"] <= tol["normal_p99"]
+            and out["distance_err_cells_max"] <= tol["distance_cells_max"] and out["distance_err_cells_p99"] <= tol["distance_cells_p99"]
+            and out["normals_nan_in_one"] == 0)))
+    return out
+
+
+def gpu_volume_host(ctx, shape, spans: np.ndarray, vcap: int | None = None, icap: int | None = None):
+    """The CUDA path's result in HOST arrays through the public C ABI (ctc_mesh_spans + ctc_sample_signs)."""
+    import cantucci_b200 as cb
+    batch, t = cb.generate_for_boxes(spans, shape, RES, ctx, vcap=vcap, icap=icap)
+    planes = cb.sample_signs(spans, shape, RES, ctx)
+    return batch.vertices, batch.indices, batch.v_off, batch.i_off, planes
+
+
 def reference_main(args):
     rank = env_int("RANK", 0)
     if rank != 0:

@@ -6,14 +6,14 @@ naive-surface-nets mesh extraction, as hand-written CUDA kernels behind a C ABI
 reference's `Shape` / `MeshBuffer` / `octree::Span` interface over that ABI.
 """
 from ._lib import (CantucciError, Context, VERTEX_DTYPE, default_context, lib, LIB_PATH)
-from .mesh import MeshBatch, MeshBuffer, Timings, generate_for_boxes, sample_grids
+from .mesh import MeshBatch, MeshBuffer, Timings, generate_for_boxes, sample_grids, sample_signs
 from .octree import Octree, Span, create_spans, spans_array, startup_tree, tile_volume
 from .shape import Mandelbulb, Shape, Sphere
 from .shape_mesh import ShapeMesh
 
 __all__ = [
     "CantucciError", "Context", "VERTEX_DTYPE", "default_context", "lib", "LIB_PATH",
-    "MeshBatch", "MeshBuffer", "Timings", "generate_for_boxes", "sample_grids",
+    "MeshBatch", "MeshBuffer", "Timings", "generate_for_boxes", "sample_grids", "sample_signs",
     "Octree", "Span", "create_spans", "spans_array", "startup_tree", "tile_volume",
     "Mandelbulb", "Shape", "Sphere", "ShapeMesh",
 ]

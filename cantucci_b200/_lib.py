@@ -68,6 +68,7 @@ EXPORTS = (
     "ctc_iteration_stats", "ctc_fp32_peak_probe",
     "ctc_ray_march", "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
     "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
+    "ctc_ctx_set_fast_band", "ctc_mesh_fixups", "ctc_fast_sign_probe", "ctc_sample_signs",
 )
 
 _lib = None
@@ -146,6 +147,14 @@ def lib() -> C.CDLL:
     L.ctc_host_register.argtypes = [vp, vp, sz]
     L.ctc_host_unregister.restype = C.c_int
     L.ctc_host_unregister.argtypes = [vp, vp]
+    L.ctc_ctx_set_fast_band.restype = C.c_int
+    L.ctc_ctx_set_fast_band.argtypes = [vp, C.c_float]
+    L.ctc_mesh_fixups.restype = C.c_int
+    L.ctc_mesh_fixups.argtypes = [vp, u64p, u64p]
+    L.ctc_sample_signs.restype = C.c_int
+    L.ctc_sample_signs.argtypes = [vp, shp, spn, sz, u32, vp]
+    L.ctc_fast_sign_probe.restype = C.c_int
+    L.ctc_fast_sign_probe.argtypes = [vp, shp, spn, sz, u32, u64p, sz]
     L.ctc_fp32_peak_probe.restype = C.c_int
     L.ctc_fp32_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _lib = L
@@ -185,6 +194,16 @@ class Context:
 
     def synchronize(self):
         self.check(lib().ctc_ctx_synchronize(self._h))
+
+    def set_fast_band(self, kappa: float = 0.0):
+        """Fast mode's sign-trust band (0 = the calibrated default)."""
+        self.check(lib().ctc_ctx_set_fast_band(self._h, kappa))
+
+    def mesh_fixups(self) -> tuple[int, int]:
+        """(samples re-evaluated exactly, of which changed sign) of the last fetched mesh result."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.check(lib().ctc_mesh_fixups(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def kernel_launches(self) -> int:
         return int(lib().ctc_kernel_launches(self._h))

@@ -49,6 +49,9 @@ struct PinnedBuf {
 
 struct EventPair { cudaEvent_t a, b; int pass; };
 
+// Defaults of the sign-trust band: see profiles/sign_probe_r2.md for the calibration.
+constexpr float kDefaultKappa = 1.0f / 262144.0f;   // 2^-18
+
 }  // namespace
 
 struct ctc_ctx {
@@ -63,8 +66,12 @@ struct ctc_ctx {
     bool timing = true;
     bool overlap = true;        // ctc_ctx_set_overlap
     bool wire_quads = false;    // ctc_ctx_set_index_wire: ctc_mesh_spans delivers packed 8-byte quad records
+    // fast mode's sign-trust band (de_device.cuh, fast_suspect_*); calibrated by ctc_fast_sign_probe
+    float kappa = kDefaultKappa;
+    bool kappa_user = false;    // set by ctc_ctx_set_fast_band: used as given, whatever max_iters
 
     // workspace
+    DevBuf suspects, suspect_count;               // fast mode: K1's suspect lists (double-buffered like the grids)
     DevBuf geom, grids, sign_bits, m_active, m_ex, m_ey, m_ez, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
     DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
     DevBuf pts_in, pts_out;
@@ -127,6 +134,16 @@ int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
         d.max_iters = s->max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s->max_iters;
         d.bailout = s->bailout;
         { volatile float b2 = s->bailout * s->bailout; d.bail2 = b2; }
+        // The band is calibrated for orbits of up to ~12 iterations (every BASELINE config with the default
+        // (6, 2.5)); longer orbits are chaotic near the surface and the first-order bound loosens by a constant
+        // per iteration, so the default band doubles every 4 further iterations (up to 2^6): profiles/sign_probe_r2.md.
+        float kappa = ctx ? ctx->kappa : kDefaultKappa;
+        if (!ctx || !ctx->kappa_user) {
+            uint64_t extra = s->max_iters > 8 ? (s->max_iters - 8 + 3) / 4 : 0;
+            if (extra > 6) extra = 6;
+            kappa *= (float)(1u << extra);
+        }
+        d.kappa = kappa;
     } else if (s->kind == CTC_SHAPE_SPHERE) {
         d.cx = s->center[0]; d.cy = s->center[1]; d.cz = s->center[2]; d.radius = s->radius;
     } else {
@@ -229,9 +246,18 @@ struct PassTimer {
     }
 };
 
+// Suspect-list capacity for a batch of `nspans` grids: 1/16 of the samples (measured: ~0.5 % are
+// suspects on the 1024^3 volume); entries beyond it are re-evaluated in place by K1 itself.
+size_t suspect_cap(size_t nspans, size_t n3) {
+    size_t cap = nspans * n3 / 16 + 4096;
+    if (cap > 0x7FFFFFF0ull) cap = 0x7FFFFFF0ull;
+    return cap;
+}
+
 template <bool kFast, int kVariant>
 void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint32_t R, uint32_t lg, float* grids,
-                   size_t stride, uint32_t nspans, size_t n3, uint32_t* sign_bits, uint32_t sign_stride) {
+                   size_t stride, uint32_t nspans, size_t n3, uint32_t* sign_bits, uint32_t sign_stride, SuspectList sl,
+                   cudaStream_t stream) {
     // R >= 32: the R^3 core and the x = R / y = R faces go to the warp-walk path; a warp walks
     // L = 64 z-samples of its 8 columns when R >= 64 (else 32): per-warp set-up paid once per 512 samples
     const size_t R2 = (size_t)R * R, R3 = R2 * R;
@@ -240,8 +266,19 @@ void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint3
     const uint32_t core_blocks = (uint32_t)((warp_blocks + 7) / 8);
     const size_t rest = core_blocks ? R2 + 3 * (size_t)R + 1 : n3;
     dim3 grid(core_blocks + (unsigned)((rest + kThreads - 1) / kThreads), nspans);
-    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, R, lg, 1.0f / (float)R, 4.0f / (float)R, grids, stride,
-                                                                             sign_bits, sign_stride, core_blocks, lgw);
+    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, stream>>>(sh, geom, R, lg, 1.0f / (float)R, 8.0f / (float)R, grids, stride,
+                                                                        sign_bits, sign_stride, core_blocks, lgw, sl);
+    ctx->launches++;
+}
+
+// Fast mode, power 8: exact re-evaluation of the suspects the K1 launch queued (sign-exact fast mode).
+void launch_fixup(ctc_ctx* ctx, const ShapeDev& sh, int variant, const SpanGeom* geom, uint32_t R, float* grids, size_t stride,
+                  uint32_t* sign_bits, uint32_t sign_stride, SuspectList sl, MeshState* st, cudaStream_t stream) {
+    const unsigned blocks = (unsigned)ctx->num_sms * 6u;
+    if (variant == kVarP8)
+        fixup_suspects_kernel<kVarP8><<<blocks, kThreads, 0, stream>>>(sh, geom, R, 1.0f / (float)R, grids, stride, sign_bits, sign_stride, sl, st);
+    else
+        fixup_suspects_kernel<kVarGeneric><<<blocks, kThreads, 0, stream>>>(sh, geom, R, 1.0f / (float)R, grids, stride, sign_bits, sign_stride, sl, st);
     ctx->launches++;
 }
 
@@ -281,11 +318,25 @@ int sample_grids_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* span
     const size_t n3 = (size_t)(R + 1) * (R + 1) * (R + 1);
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
     const int variant = shape_variant(shape);
-    for (size_t s0 = 0; s0 < nspans; s0 += 32768) {
-        const uint32_t cnt = (uint32_t)((nspans - s0) < 32768 ? (nspans - s0) : 32768);
-#define CALL(F, V) launch_sample<F, V>(ctx, sh, ctx->geom.as<SpanGeom>() + s0, R, lg, d_grids + s0 * n3, n3, cnt, n3, nullptr, 0u)
+    const bool listed = fast && variant == kVarP8;     // K1 queues suspects for the exact re-evaluation
+    // launch batches: gridDim.y limit, and the suspect list of a batch must fit its u32 counter
+    size_t per = 32768;
+    while (per > 1 && per * n3 > (size_t)0x7FFFFFF0ull) per /= 2;
+    SuspectList sl{nullptr, nullptr, 0u};
+    if (listed) {
+        const size_t cap = suspect_cap(per < nspans ? per : nspans, n3);
+        CK(ctx->suspects.ensure(cap * sizeof(uint2)));
+        CK(ctx->suspect_count.ensure(2 * sizeof(unsigned int)));
+        sl = SuspectList{ctx->suspects.as<uint2>(), ctx->suspect_count.as<unsigned int>(), (uint32_t)cap};
+    }
+    for (size_t s0 = 0; s0 < nspans; s0 += per) {
+        const uint32_t cnt = (uint32_t)((nspans - s0) < per ? (nspans - s0) : per);
+        if (listed) CK(cudaMemsetAsync(sl.count, 0, sizeof(unsigned int), ctx->stream));
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, ctx->geom.as<SpanGeom>() + s0, R, lg, d_grids + s0 * n3, n3, cnt, n3, nullptr, 0u, sl, ctx->stream)
         DISPATCH(fast, variant, CALL);
 #undef CALL
+        if (listed)
+            launch_fixup(ctx, sh, variant, ctx->geom.as<SpanGeom>() + s0, R, d_grids + s0 * n3, n3, nullptr, 0u, sl, nullptr, ctx->stream);
     }
     CK(cudaGetLastError());
     return CTC_OK;
@@ -370,10 +421,18 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     CK(ctx->word_vpre.ensure(words * 4)); CK(ctx->word_qpre.ensure(words * 4));
     CK(ctx->chunk_counts.ensure(chunks * sizeof(uint2))); CK(ctx->chunk_pre.ensure(chunks * sizeof(uint2)));
     CK(ctx->cell_of.ensure((size_t)(cell_cap ? cell_cap : 1) * 4));
-    Masks m{ctx->m_active.as<uint32_t>(), ctx->m_ex.as<uint32_t>(), ctx->m_ey.as<uint32_t>(), ctx->m_ez.as<uint32_t>()};
-
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
     const int variant = shape_variant(shape);
+    // fast mode, power 8: K1 queues the samples whose sign cannot be trusted; the extraction stream
+    // re-evaluates them exactly before it classifies (lists double-buffered like the grids)
+    const bool listed = fast && variant == kVarP8;
+    const size_t list_cap = listed ? suspect_cap(G, gp.n3) : 0;
+    if (listed) {
+        CK(ctx->suspects.ensure(nbuf * list_cap * sizeof(uint2)));
+        CK(ctx->suspect_count.ensure(2 * sizeof(unsigned int)));
+    }
+    Masks m{ctx->m_active.as<uint32_t>(), ctx->m_ex.as<uint32_t>(), ctx->m_ey.as<uint32_t>(), ctx->m_ez.as<uint32_t>()};
+
     const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
     // Launch groups.  With the copy pipeline on, the first groups are small (64, 128, 256, ... spans)
     // so that the device->host / peer copies start almost immediately instead of after a full group,
@@ -434,10 +493,15 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         if (two_streams && gi >= 2) CK(cudaStreamWaitEvent(sA, ctx->ext_done[gi - 2], 0));
         const uint32_t cnt = groups[gi].second;
         const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
+        SuspectList sl{nullptr, nullptr, 0u};
+        if (listed)
+            sl = SuspectList{ctx->suspects.as<uint2>() + (gi % nbuf) * list_cap,
+                             ctx->suspect_count.as<unsigned int>() + (gi % nbuf), (uint32_t)list_cap};
         {   // pass 1
             PassTimer t(ctx, 0, sA);
             CK(cudaMemsetAsync(sign_bits, 0, (size_t)cnt * sign_stride * 4, sA));
-#define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3, sign_bits, sign_stride)
+            if (listed) CK(cudaMemsetAsync(sl.count, 0, sizeof(unsigned int), sA));
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3, sign_bits, sign_stride, sl, sA)
             DISPATCH(fast, variant, CALL);
 #undef CALL
         }
@@ -446,8 +510,9 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
             CK(cudaStreamWaitEvent(sE, ctx->k1_done[gi], 0));
         }
         dim3 cgrid(gp.chunks_per_span, cnt);
-        {   // pass 2: classify, scan, vertices
+        {   // pass 2: (fast mode: sign repair,) classify, scan, vertices
             PassTimer t(ctx, 1, sE);
+            if (listed) launch_fixup(ctx, sh, variant, geom, R, grids, gp.n3, sign_bits, sign_stride, sl, st, sE);
             classify_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
                                                                 gp.chunk_words, m, ctx->chunk_counts.as<uint2>());
             scan_chunks_kernel<<<1, kScanThreads, 0, sE>>>(
@@ -561,7 +626,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->m_ex, &c->m_ey, &c->m_ez, &c->sign_bits, &c->chunk_counts,
                       &c->chunk_pre, &c->word_vpre, &c->word_qpre, &c->cell_of, &c->state, &c->out_v, &c->out_idx,
-                      &c->off_v, &c->off_i, &c->pts_in, &c->pts_out})
+                      &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
     c->h_geom.release(); c->h_state.release(); c->h_tables.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -897,6 +962,109 @@ int ctc_iteration_stats(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* sp
     CK(cudaMemcpyAsync(h, ctx->pts_out.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    return CTC_OK;
+}
+
+int ctc_ctx_set_fast_band(ctc_ctx* ctx, float kappa) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!(kappa >= 0.0f)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "kappa must be >= 0");
+    ctx->kappa = kappa > 0.0f ? kappa : kDefaultKappa;
+    ctx->kappa_user = kappa > 0.0f;
+    return CTC_OK;
+}
+
+int ctc_mesh_fixups(ctc_ctx* ctx, uint64_t* suspects, uint64_t* sign_fixups) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->h_state.p) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "no mesh result has been fetched on this context");
+    const MeshState* st = static_cast<const MeshState*>(ctx->h_state.p);
+    if (suspects) *suspects = st->suspects;
+    if (sign_fixups) *sign_fixups = st->sign_fixups;
+    return CTC_OK;
+}
+
+int ctc_sample_signs(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                     uint32_t* planes) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh; uint32_t lg;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    rc = check_spans(ctx, spans, nspans, resolution, &lg); if (rc) return rc;
+    if (nspans == 0) return CTC_OK;
+    if (!planes) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "planes is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = upload_geom(ctx, spans, nspans, resolution); if (rc) return rc;
+    const size_t n3 = (size_t)(resolution + 1) * (resolution + 1) * (resolution + 1);
+    const size_t words = (n3 + 31) / 32;
+    const uint32_t sign_stride = (uint32_t)(words + 1);
+    size_t per = (1ull << 30) / (n3 * 4);
+    if (per < 1) per = 1;
+    if (per > nspans) per = nspans;
+    if (per > 32768) per = 32768;
+    CK(ctx->grids.ensure(per * n3 * 4));
+    CK(ctx->sign_bits.ensure(per * (size_t)sign_stride * 4));
+    const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
+    const int variant = shape_variant(shape);
+    const bool listed = fast && variant == kVarP8;
+    SuspectList sl{nullptr, nullptr, 0u};
+    if (listed) {
+        const size_t cap = suspect_cap(per, n3);
+        CK(ctx->suspects.ensure(cap * sizeof(uint2)));
+        CK(ctx->suspect_count.ensure(2 * sizeof(unsigned int)));
+        sl = SuspectList{ctx->suspects.as<uint2>(), ctx->suspect_count.as<unsigned int>(), (uint32_t)cap};
+    }
+    for (size_t s0 = 0; s0 < nspans; s0 += per) {
+        const uint32_t cnt = (uint32_t)((nspans - s0) < per ? (nspans - s0) : per);
+        const SpanGeom* geom = ctx->geom.as<SpanGeom>() + s0;
+        CK(cudaMemsetAsync(ctx->sign_bits.p, 0, (size_t)cnt * sign_stride * 4, ctx->stream));
+        if (listed) CK(cudaMemsetAsync(sl.count, 0, sizeof(unsigned int), ctx->stream));
+#define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, resolution, lg, ctx->grids.as<float>(), n3, cnt, n3, ctx->sign_bits.as<uint32_t>(), sign_stride, sl, ctx->stream)
+        DISPATCH(fast, variant, CALL);
+#undef CALL
+        if (listed)
+            launch_fixup(ctx, sh, variant, geom, resolution, ctx->grids.as<float>(), n3, ctx->sign_bits.as<uint32_t>(), sign_stride, sl, nullptr, ctx->stream);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy2DAsync(planes + s0 * words, words * 4, ctx->sign_bits.p, (size_t)sign_stride * 4, words * 4, cnt,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return CTC_OK;
+}
+
+int ctc_fast_sign_probe(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                        uint64_t* out, size_t out_words) {
+    if (!ctx || !out) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh; uint32_t lg;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    rc = check_spans(ctx, spans, nspans, resolution, &lg); if (rc) return rc;
+    if (shape_variant(shape) != kVarP8) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "the sign probe covers the power-8 path");
+    constexpr size_t kDumpWords = (size_t)kProbeDump * 6;      // 12 floats per record
+    constexpr size_t kTotal = (size_t)kProbeWords + 1 + kDumpWords;
+    if (out_words < kTotal) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "out too small (ctc_fast_sign_probe needs 489 words)");
+    for (size_t i = 0; i < out_words; ++i) out[i] = 0;
+    if (nspans == 0) return CTC_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = upload_geom(ctx, spans, nspans, resolution); if (rc) return rc;
+    CK(ctx->pts_out.ensure(kTotal * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->pts_out.p, 0, kTotal * sizeof(unsigned long long), ctx->stream));
+    unsigned long long* d_out = ctx->pts_out.as<unsigned long long>();
+    unsigned int* d_cnt = reinterpret_cast<unsigned int*>(d_out + kProbeWords);
+    float* d_dump = reinterpret_cast<float*>(d_out + kProbeWords + 1);
+    const size_t n3 = (size_t)(resolution + 1) * (resolution + 1) * (resolution + 1);
+    for (size_t s0 = 0; s0 < nspans; s0 += 32768) {
+        const uint32_t cnt = (uint32_t)((nspans - s0) < 32768 ? (nspans - s0) : 32768);
+        dim3 grid((unsigned)((n3 + kThreads - 1) / kThreads), cnt);
+        fast_sign_probe_kernel<<<grid, kThreads, 0, ctx->stream>>>(sh, ctx->geom.as<SpanGeom>() + s0, resolution, lg,
+                                                                   1.0f / (float)resolution, d_out, d_dump, d_cnt);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->pts_out.p, kTotal * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return CTC_OK;
 }
 

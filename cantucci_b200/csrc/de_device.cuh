@@ -25,6 +25,7 @@ struct ShapeDev {
     uint32_t max_iters;  // clamped to 2^32-1 on the host
     float    bailout;
     float    bail2;      // bailout * bailout (host, IEEE): the FAST path tests squared radii
+    float    kappa;      // FAST: sign-trust band |r^2 - 1| <= kappa * max dr (see fast_suspect_*)
     float    cx, cy, cz, radius;
 };
 
@@ -167,7 +168,7 @@ __device__ __noinline__ float rotate_on_z_axis_exact(uint32_t P, float z, float 
 // Mandelbulb::<P>::min_distance_from (mandelbulb.rs:59-79)
 template <bool kP8>
 __device__ __forceinline__ float mandelbulb_de_exact(const ShapeDev& s, float px, float py, float pz,
-                                                     uint32_t* iters_out = nullptr) {
+                                                     uint32_t* iters_out = nullptr, float* r_out = nullptr) {
     using M = MathExact;
     const uint32_t P = kP8 ? 8u : s.power;
     const float fP = (float)P;
@@ -192,6 +193,7 @@ __device__ __forceinline__ float mandelbulb_de_exact(const ShapeDev& s, float px
         zx = M::add(nx, px); zy = M::add(ny, py); zz = M::add(nz, pz);
     }
     if (iters_out) *iters_out = it;
+    if (r_out) *r_out = r;
     const float ln_r = M::mul(M::log(r), r);
     return canonical_x86_nan(M::div(M::mul(0.5f, ln_r), dr));
 }
@@ -260,12 +262,47 @@ __device__ __forceinline__ float mandelbulb_de_exact_p8_column(const ShapeDev& s
 }
 
 // ---------------------------------------------------------------------------
-// FAST: same recurrence, FMA-contracted and re-associated
+// FAST: same recurrence, FMA-contracted and re-associated.
+//
+// The power-8 step is written ONCE over a lane-vector type V.  V = float evaluates one sample per
+// thread; V = float2 evaluates two samples per thread in sm_100's packed FP32 instructions
+// (FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE-rounded results).  K1 and E3 are bound by issue
+// slots in scalar form (ncu: issue 94 %, FMA pipe 67 %); in packed form the FMA pipe is the bound.
+// Every operation is an explicit round-to-nearest intrinsic, so both instantiations produce the same
+// bits for the same sample (the scalar form is what the tail paths, K3 and the probes run).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float fast_rcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float fast_sqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float fast_rsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float fast_lg2(float a) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+
+template <class V> struct Lanes;
+
+template <> struct Lanes<float> {
+    __device__ static __forceinline__ float bc(float a) { return a; }
+    __device__ static __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    __device__ static __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    __device__ static __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    __device__ static __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    __device__ static __forceinline__ float fms(float a, float b, float c) { return __fmaf_rn(a, b, -c); }   // a*b - c
+    __device__ static __forceinline__ float rsqrt(float a) { return fast_rsqrt(a); }
+    __device__ static __forceinline__ float sqrt(float a) { return fast_sqrt(a); }
+    __device__ static __forceinline__ float vmin(float a, float b) { return fminf(a, b); }
+    __device__ static __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+};
+
+template <> struct Lanes<float2> {
+    __device__ static __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+    __device__ static __forceinline__ float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+    __device__ static __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+    __device__ static __forceinline__ float2 sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+    __device__ static __forceinline__ float2 fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+    __device__ static __forceinline__ float2 fms(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, make_float2(-c.x, -c.y)); }
+    __device__ static __forceinline__ float2 rsqrt(float2 a) { return make_float2(fast_rsqrt(a.x), fast_rsqrt(a.y)); }
+    __device__ static __forceinline__ float2 sqrt(float2 a) { return make_float2(fast_sqrt(a.x), fast_sqrt(a.y)); }
+    __device__ static __forceinline__ float2 vmin(float2 a, float2 b) { return make_float2(fminf(a.x, b.x), fminf(a.y, b.y)); }
+    __device__ static __forceinline__ float2 vmax(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+};
 
 // (a + i b)^n by binary exponentiation, n >= 1 warp-uniform
 __device__ __forceinline__ void cpow(float a, float b, uint32_t n, float& re, float& im) {
@@ -292,124 +329,350 @@ __device__ __forceinline__ void cpow(float a, float b, uint32_t n, float& re, fl
 //     X = A (cos 8phi - 2 v^8),  Y = A sin 8phi   with (u, v) = (x, y) / w = e^{i phi}
 // (the "- 2 v^8" is the reference's "- y8" where the real part of (x + i y)^8 has "+ y8"; it is
 // reproduced, not fixed).  Working on the unit vector (u, v) removes the division by w^8, which
-// underflows near the z axis and injects inf/NaN into the reference's own arithmetic; w2 is clamped
-// before the rsqrt, so the step is finite for every finite input.
-// 28 FMA-pipe instructions + 1 MUFU per step (+ 4 and 1 MUFU for dr) against 75 algorithmic flops.
-__device__ __forceinline__ void p8_azimuth(float x, float y, float w2, float& iw, float& c8, float& s8h) {
-    iw = fast_rsqrt(fmaxf(w2, 1e-36f));
-    const float u = x * iw, v = y * iw;
-    const float v2 = v * v;
-    const float c2 = fmaf(u, u, -v2);                       // cos 2phi
-    const float s2 = 2.0f * (u * v);                        // sin 2phi
-    const float c4 = fmaf(c2, c2, -(s2 * s2));              // cos 4phi
-    const float q4 = 2.0f * (s2 * c2);                      // sin 4phi
-    const float v4 = v2 * v2;
-    c8 = fmaf(-2.0f, v4 * v4, fmaf(c4, c4, -(q4 * q4)));    // cos 8phi - 2 v^8
-    s8h = c4 * q4;                                          // sin 8phi / 2
+// underflows near the z axis and injects inf/NaN into the reference's own arithmetic.  The squarings
+// carry NEGATED half-angle sines (m4n = -2 sin, q4n = -sin 4x) so that no operand needs a separate
+// negation or doubling: 15 + 10 + 4 FMA-pipe operations per step, + 4 for the magnitude and 5 for dr
+// = 38 against 75 algorithmic flops.
+template <class V>
+__device__ __forceinline__ void p8_azimuth(V x, V y, V iw, V& c8, V& s8hn) {
+    using L = Lanes<V>;
+    const V u = L::mul(x, iw), v = L::mul(y, iw);
+    const V m = L::mul(u, v);                               // sin 2phi / 2
+    const V v2 = L::mul(v, v);
+    const V c2 = L::fms(u, u, v2);                          // cos 2phi
+    const V cc = L::mul(c2, c2);
+    const V m4n = L::mul(m, L::bc(-4.0f));                  // -2 sin 2phi
+    const V c4 = L::fma(m4n, m, cc);                        // cos 4phi = c2^2 - s2^2
+    const V q4n = L::mul(m4n, c2);                          // -sin 4phi
+    const V v4 = L::mul(v2, v2);
+    const V v8 = L::mul(v4, v4);
+    const V t = L::mul(q4n, q4n);
+    const V c8a = L::fms(c4, c4, t);                        // cos 8phi
+    c8 = L::fma(v8, L::bc(-2.0f), c8a);                     // cos 8phi - 2 v^8
+    s8hn = L::mul(c4, q4n);                                 // -sin 8phi / 2
 }
 
-__device__ __forceinline__ void p8_elevation(float z, float z2, float w, float w2, float& A, float& Zh) {
-    const float s2 = 2.0f * (z * w);
-    const float c2 = z2 - w2;
-    const float c4 = fmaf(c2, c2, -(s2 * s2));
-    const float q4 = 2.0f * (s2 * c2);
-    A = fmaf(c4, c4, -(q4 * q4));                           // Re (z + i w)^8
-    Zh = c4 * q4;                                           // Im (z + i w)^8 / 2
+template <class V>
+__device__ __forceinline__ void p8_elevation(V z, V z2, V w, V w2, V& A, V& Zhn) {
+    using L = Lanes<V>;
+    const V m = L::mul(z, w);
+    const V c2 = L::sub(z2, w2);
+    const V cc = L::mul(c2, c2);
+    const V m4n = L::mul(m, L::bc(-4.0f));
+    const V c4 = L::fma(m4n, m, cc);
+    const V q4n = L::mul(m4n, c2);
+    const V t = L::mul(q4n, q4n);
+    A = L::fms(c4, c4, t);                                  // Re (z + i w)^8
+    Zhn = L::mul(c4, q4n);                                  // -Im (z + i w)^8 / 2
 }
 
-__device__ __forceinline__ void rotate_p8_fast(float x, float y, float z, float z2, float w2,
-                                               float px, float py, float pz, float& ox, float& oy, float& oz) {
-    float iw, c8, s8h, A, Zh;
-    p8_azimuth(x, y, w2, iw, c8, s8h);
-    p8_elevation(z, z2, w2 * iw, w2, A, Zh);
-    ox = fmaf(A, c8, px);
-    oy = fmaf(2.0f * A, s8h, py);
-    oz = fmaf(2.0f, Zh, pz);
+// dr = 8 r^7 dr + 1 from r^2; r^7 is kept for the polar-stretch bookkeeping
+template <class V>
+__device__ __forceinline__ V p8_dr(V r2, V dr, V& r7) {
+    using L = Lanes<V>;
+    const V r4 = L::mul(r2, r2);
+    r7 = L::mul(L::mul(r4, r2), L::sqrt(r2));
+    return L::fma(L::mul(r7, L::bc(8.0f)), dr, L::bc(1.0f));
 }
 
-// FAST path for a sample ON the z axis (px == py == 0 exactly): the orbit never leaves the axis
-// (rotate_on_z_axis, mandelbulb.rs:114-126): z' = |z|^P cos(P theta) + pz with theta in {0, pi},
-// i.e. z' = z^P + pz for even P and the same for odd P (cos(P pi) = -1 flips the sign back).
-// The origin is 0/0 in the reference -> NaN.  Cold: one lattice column per dense grid at most.
-__device__ __noinline__ float mandelbulb_de_fast_on_axis(uint32_t P, uint32_t max_iters, float bailout, float pz) {
-    float zz = pz, dr = 1.0f, r = 0.0f;
-    for (uint32_t it = 0; it < max_iters; ++it) {
-        r = fabsf(zz);
-        if (r > bailout) break;
-        if (r == 0.0f) return __int_as_float(0xFFC00000);
-        float rp1 = 1.0f;
-        { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
-        dr = fmaf((float)P * rp1, dr, 1.0f);
-        const float rp = rp1 * r;
-        zz = ((zz < 0.0f && (P & 1u)) ? -rp : rp) + pz;
+// z <- z^8 + p (the rotate and the "+ p" of mandelbulb.rs:74 in one FMA each).  A = Re (z + i w)^8
+// (the new distance from the z axis before "+ p") and iw = 1 / w go to the polar-stretch bookkeeping.
+template <class V>
+__device__ __forceinline__ void p8_step(V& zx, V& zy, V& zz, V z2, V w2, V px, V py, V pz, V& A, V& iw) {
+    using L = Lanes<V>;
+    iw = L::rsqrt(w2);
+    V c8, s8hn, Zhn;
+    p8_azimuth<V>(zx, zy, iw, c8, s8hn);
+    p8_elevation<V>(zz, z2, L::mul(w2, iw), w2, A, Zhn);
+    zx = L::fma(A, c8, px);
+    zy = L::fma(L::mul(A, L::bc(-2.0f)), s8hn, py);
+    zz = L::fma(L::bc(-2.0f), Zhn, pz);
+}
+
+// Extra error amplification of one step near the poles.  The triplex power is not conformal: a
+// perturbation along the azimuth is stretched by 8 |A| / w (A = Re (z + i w)^8, the new distance from
+// the z axis) where the radial and polar directions see 8 r^7 -- up to 8 r / w more, and dr (= the
+// reference's own derivative estimate) only carries 8 r^7.  Kept in the log domain on raw float bits
+// (2^23 per octave, piecewise-linear lg): max(0, lg |A| + lg 1/w - lg r^7) -- four ALU-pipe
+// instructions per sample and iteration, none on the FMA pipe that bounds the kernel.
+__device__ __forceinline__ int polar_stretch_log(float A, float iw, float r7) {
+    const int t = (int)(__float_as_uint(A) & 0x7fffffffu) + (int)__float_as_uint(iw) - (int)__float_as_uint(r7);
+    return max(t - 0x3f800000, 0);
+}
+// An iterate within ~1e-3 r of the z axis stretches by >= 2^10 in that one step: the accumulated
+// stretch doubles as the "touched the z axis" test (the reference's w^8 underflows there, its arithmetic
+// turns inf/NaN, and the fast path's 1/w is inf on the axis itself).
+constexpr int kAxisLog = 10 << 23;
+// accumulated stretch as a float factor (same piecewise-linear exponential; clamped far below overflow)
+__device__ __forceinline__ float polar_factor(int logp) { return __int_as_float(0x3f800000 + min(logp, 0x20000000)); }
+
+// 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
+__device__ __forceinline__ float de_fast_epilogue(float r2, float dr) {
+    return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
+}
+
+// ---------------------------------------------------------------------------
+// Can the SIGN of a fast evaluation be trusted?  (DESIGN.md "sign-exact fast mode")
+//
+// The mesher's topology is a function of f32::is_sign_positive() of every sample, and the sign of
+// 0.5 ln(r) r / dr is decided by ONE comparison: a sample that leaves through `r > bailout` is
+// positive; one that runs all max_iters iterations is negative iff its last radius is < 1.  (A
+// borderline bailout decision cannot flip the sign: with r ~ bailout the next radius is ~ bailout^8.)
+// The fast path's r^2 differs from the reference's by at most ~ kappa * dr: dr obeys the same
+// recurrence as a first-order bound on the orbit's accumulated rounding error
+// (e' = 8 r^7 e + eta  vs  dr' = 8 r^7 dr + 1).  A sample is SUSPECT, and re-evaluated with the
+// exact-order IEEE arithmetic, when
+//   * it did not escape and |r^2 - 1| <= kappa * max_k dr_k * S  (sign of ln r not certain), or
+//   * it escaped but kappa * max_k dr_k * S is O(1)              (the orbit itself is not certain), or
+//   * S >= 2^10: some iterate came within ~1e-3 r of the z axis  (the reference's w^8 underflows there and
+//                                                                 its arithmetic turns inf/NaN), or
+//   * anything is NaN (all tests are written so that NaN is suspect).
+// S is the accumulated polar stretch (polar_stretch_log): near the poles the map stretches azimuthal
+// perturbations up to 8 r / w more than the 8 r^7 that dr carries; without S four of the 1.1 G samples
+// of the benched volume escape the band at any useful kappa, with it none does (profiles/sign_probe_r2.md).
+// kappa is calibrated on the GPU (ctc_fast_sign_probe, profiles/sign_probe_r2.md).
+// kBand = false keeps only the axis/NaN rules (E3: values, not signs).
+// ---------------------------------------------------------------------------
+template <bool kBand>
+__device__ __forceinline__ bool fast_suspect_escaped(const ShapeDev& s, float drmax, int logp) {
+    return logp >= kAxisLog || (kBand && !(s.kappa * drmax * polar_factor(logp) < 4.0f));
+}
+template <bool kBand>
+__device__ __forceinline__ bool fast_suspect_inside(const ShapeDev& s, float r2, float drmax, int logp) {
+    if (!kBand) return logp >= kAxisLog || !(r2 == r2);
+    return logp >= kAxisLog || !(fabsf(r2 - 1.0f) > s.kappa * drmax * polar_factor(logp));
+}
+
+// FAST power-8 DE of one sample.
+struct FastInfo { float r2, dr, drmax, wmin; uint32_t escaped; float polar; float wrmin; };   // probe output (ctc_fast_sign_probe)
+
+// FAST power-8 DE of one sample.
+template <bool kBand>
+__device__ __forceinline__ float mandelbulb_de_fast_p8(const ShapeDev& s, float px, float py, float pz, bool& suspect) {
+    using L = Lanes<float>;
+    float zx = px, zy = py, zz = pz, dr = 1.0f, drmax = 1.0f, r2;
+    int logp = 0;
+    uint32_t left = s.max_iters;                 // >= 1 (checked on the host, mandelbulb.rs:20)
+    for (;;) {
+        const float z2 = L::mul(zz, zz);
+        const float w2 = L::fma(zx, zx, L::mul(zy, zy));
+        r2 = L::add(w2, z2);
+        if (r2 > s.bail2) {                      // r > bailout, on squares
+            suspect = fast_suspect_escaped<kBand>(s, drmax, logp);
+            return de_fast_epilogue(r2, dr);
+        }
+        float r7, A, iw;
+        dr = p8_dr<float>(r2, dr, r7);
+        drmax = fmaxf(drmax, dr);
+        if (--left == 0u) break;                 // the reference's last rotate is dead work
+        p8_step<float>(zx, zy, zz, z2, w2, px, py, pz, A, iw);
+        logp += polar_stretch_log(A, iw, r7);
     }
-    return canonical_x86_nan(0.5f * __logf(r) * r / dr);
+    suspect = fast_suspect_inside<kBand>(s, r2, drmax, logp);
+    return de_fast_epilogue(r2, dr);
 }
 
-// kCheckAxis = false: the caller guarantees (px, py) != (0, 0) (K1 tests it once per warp).
-template <bool kP8, bool kCheckAxis = true>
-__device__ __forceinline__ float mandelbulb_de_fast(const ShapeDev& s, float px, float py, float pz) {
-    const uint32_t P = kP8 ? 8u : s.power;
-    if (kCheckAxis && px == 0.0f && py == 0.0f) return mandelbulb_de_fast_on_axis(P, s.max_iters, s.bailout, pz);
+// The same evaluation, instrumented for ctc_fast_sign_probe (identical operations, identical bits).
+__device__ __forceinline__ float mandelbulb_de_fast_p8_probe(const ShapeDev& s, float px, float py, float pz, FastInfo& info) {
+    using L = Lanes<float>;
+    float zx = px, zy = py, zz = pz, dr = 1.0f, drmax = 1.0f, r2;
+    float wmin = __int_as_float(0x7f800000), wrmin = 1.0f;
+    int logp = 0;
+    uint32_t left = s.max_iters, escaped = 0u;
+    for (;;) {
+        const float z2 = L::mul(zz, zz);
+        const float w2 = L::fma(zx, zx, L::mul(zy, zy));
+        r2 = L::add(w2, z2);
+        wmin = fminf(wmin, w2);
+        if (r2 > s.bail2) { escaped = 1u; break; }
+        wrmin = fminf(wrmin, w2 / r2);
+        const float r4 = L::mul(r2, r2);
+        const float r7 = L::mul(L::mul(r4, r2), L::sqrt(r2));
+        dr = L::fma(L::mul(r7, 8.0f), dr, 1.0f);
+        drmax = fmaxf(drmax, dr);
+        if (--left == 0u) break;
+        const float iw = L::rsqrt(w2);
+        float c8, s8hn, A, Zhn;
+        p8_azimuth<float>(zx, zy, iw, c8, s8hn);
+        p8_elevation<float>(zz, z2, L::mul(w2, iw), w2, A, Zhn);
+        logp += polar_stretch_log(A, iw, r7);
+        zx = L::fma(A, c8, px);
+        zy = L::fma(L::mul(A, -2.0f), s8hn, py);
+        zz = L::fma(-2.0f, Zhn, pz);
+    }
+    info = FastInfo{r2, dr, drmax, wmin, escaped, polar_factor(logp), wrmin};
+    return de_fast_epilogue(r2, dr);
+}
+
+// Two samples per thread.  State of a pair evaluation: the live iterate, and the snapshot of
+// (r^2, dr, max dr, polar stretch) a half leaves behind when it escapes.  An escaped half is parked on
+// NaN (its `+ p` operand), so it never escapes again, and BOTH distances are computed once, in packed
+// form, after the loop: the escape path is a handful of moves.
+struct PairP8 {
+    float2 px, py, pz;        // the two sample points
+    float2 zx, zy, zz;        // current iterate
+    float2 dr, drmax;
+    int2 logp;                // accumulated polar stretch (log domain)
+    float2 r2s, drs, dms;     // snapshot at escape: r^2, dr, max dr
+    int2 lps;
+    uint32_t esc;             // bit k: half k escaped
+};
+
+#define CTC_PAIR_ESCAPE(H, BIT)                                                                  \
+    if (r2.H > bail2) {                                                                          \
+        st.r2s.H = r2.H; st.drs.H = st.dr.H; st.dms.H = st.drmax.H; st.lps.H = st.logp.H;        \
+        st.esc |= BIT;                                                                           \
+        st.px.H = __int_as_float(0x7fffffff);                                                    \
+    }
+
+// Runs the remaining iterations.  On entry (zx, zy, zz) hold the current iterate of both halves and
+// `left` >= 1 radius tests remain.  Returns the last r^2 of the halves that did not escape.
+__device__ __forceinline__ float2 p8_pair_loop(PairP8& st, float bail2, uint32_t left) {
+    using L = Lanes<float2>;
+    float2 r2;
+    for (;;) {
+        const float2 z2 = L::mul(st.zz, st.zz);
+        const float2 w2 = L::fma(st.zx, st.zx, L::mul(st.zy, st.zy));
+        r2 = L::add(w2, z2);
+        if ((r2.x > bail2) | (r2.y > bail2)) {
+            CTC_PAIR_ESCAPE(x, 1u)
+            CTC_PAIR_ESCAPE(y, 2u)
+            if (st.esc == 3u) break;
+        }
+        float2 r7, A, iw;
+        st.dr = p8_dr<float2>(r2, st.dr, r7);
+        st.drmax = L::vmax(st.drmax, st.dr);
+        if (--left == 0u) break;
+        p8_step<float2>(st.zx, st.zy, st.zz, z2, w2, st.px, st.py, st.pz, A, iw);
+        st.logp.x += polar_stretch_log(A.x, iw.x, r7.x);
+        st.logp.y += polar_stretch_log(A.y, iw.y, r7.y);
+    }
+    return r2;
+}
+
+// Both distances and the suspect bits from the final state (r2 = last r^2 of the non-escaped halves).
+template <bool kBand>
+__device__ __forceinline__ float2 p8_pair_finish(const ShapeDev& s, const PairP8& st, float2 r2, uint32_t& suspect) {
+    using L = Lanes<float2>;
+    const bool ea = st.esc & 1u, eb = st.esc & 2u;
+    const float2 R2 = make_float2(ea ? st.r2s.x : r2.x, eb ? st.r2s.y : r2.y);
+    const float2 DR = make_float2(ea ? st.drs.x : st.dr.x, eb ? st.drs.y : st.dr.y);
+    const float2 DM = make_float2(ea ? st.dms.x : st.drmax.x, eb ? st.dms.y : st.drmax.y);
+    const int lpa = ea ? st.lps.x : st.logp.x, lpb = eb ? st.lps.y : st.logp.y;
+    // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
+    const float2 lg = make_float2(fast_lg2(R2.x), fast_lg2(R2.y));
+    const float2 rc = make_float2(fast_rcp(DR.x), fast_rcp(DR.y));
+    const float2 d = L::mul(L::mul(L::mul(lg, L::bc(0.25f * 0.69314718056f)), L::sqrt(R2)), rc);
+    uint32_t su = (lpa >= kAxisLog ? 1u : 0u) | (lpb >= kAxisLog ? 2u : 0u);
+    if (kBand) {
+        const float2 bound = L::mul(L::mul(DM, L::bc(s.kappa)), make_float2(polar_factor(lpa), polar_factor(lpb)));
+        const float ma = ea ? 4.0f : fabsf(R2.x - 1.0f), mb = eb ? 4.0f : fabsf(R2.y - 1.0f);
+        if (!(ma > bound.x)) su |= 1u;
+        if (!(mb > bound.y)) su |= 2u;
+    } else {
+        if (!(R2.x == R2.x)) su |= 1u;
+        if (!(R2.y == R2.y)) su |= 2u;
+    }
+    suspect = su;
+    return d;
+}
+
+// FAST power-8 DE of two arbitrary points.  Bit k of `suspect`: the result of half k needs the exact path.
+template <bool kBand>
+__device__ __forceinline__ float2 mandelbulb_de_fast_p8_pair(const ShapeDev& s, float2 px, float2 py, float2 pz, uint32_t& suspect) {
+    PairP8 st;
+    st.px = px; st.py = py; st.pz = pz; st.zx = px; st.zy = py; st.zz = pz;
+    st.dr = make_float2(1.0f, 1.0f); st.drmax = st.dr; st.logp = make_int2(0, 0);
+    st.r2s = st.dr; st.drs = st.dr; st.dms = st.dr; st.lps = st.logp; st.esc = 0u;
+    const float2 r2 = p8_pair_loop(st, s.bail2, s.max_iters);
+    return p8_pair_finish<kBand>(s, st, r2, suspect);
+}
+
+// FAST power-8 DE along a lattice COLUMN: K1 walks z with (px, py) fixed, so the first iteration's
+// azimuth factors (which depend on x and y only) are computed once per column and only the elevation
+// half of the first step is per sample.  Same operations on the same operands as the point form.
+struct ColumnFastP8 { float w2, w, iw, c8, s8hn; };
+
+__device__ __forceinline__ ColumnFastP8 column_fast_p8(float px, float py) {
+    using L = Lanes<float>;
+    ColumnFastP8 c;
+    c.w2 = L::fma(px, px, L::mul(py, py));
+    c.iw = L::rsqrt(c.w2);
+    p8_azimuth<float>(px, py, c.iw, c.c8, c.s8hn);
+    c.w = L::mul(c.w2, c.iw);
+    return c;
+}
+
+template <bool kBand>
+__device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeDev& s, float px_, float py_, float2 pz,
+                                                                    const ColumnFastP8& c, uint32_t& suspect) {
+    using L = Lanes<float2>;
+    const float bail2 = s.bail2;
+    PairP8 st;
+    st.px = L::bc(px_); st.py = L::bc(py_); st.pz = pz;
+    st.dr = L::bc(1.0f); st.drmax = st.dr; st.logp = make_int2(0, 0);
+    st.r2s = st.dr; st.drs = st.dr; st.dms = st.dr; st.lps = st.logp; st.esc = 0u;
+    uint32_t left = s.max_iters;
+    const float2 z2 = L::mul(pz, pz);
+    const float2 w2 = L::bc(c.w2);
+    float2 r2 = L::add(w2, z2);
+    if ((r2.x > bail2) | (r2.y > bail2)) {
+        CTC_PAIR_ESCAPE(x, 1u)
+        CTC_PAIR_ESCAPE(y, 2u)
+    }
+    if (st.esc != 3u) {
+        float2 r7;
+        st.dr = p8_dr<float2>(r2, st.dr, r7);
+        st.drmax = L::vmax(st.drmax, st.dr);
+        if (--left != 0u) {
+            float2 A, Zhn;
+            p8_elevation<float2>(pz, z2, L::bc(c.w), w2, A, Zhn);
+            st.zx = L::fma(A, L::bc(c.c8), st.px);
+            st.zy = L::fma(L::mul(A, L::bc(-2.0f)), L::bc(c.s8hn), st.py);
+            st.zz = L::fma(L::bc(-2.0f), Zhn, pz);
+            st.logp.x = polar_stretch_log(A.x, c.iw, r7.x);
+            st.logp.y = polar_stretch_log(A.y, c.iw, r7.y);
+            r2 = p8_pair_loop(st, bail2, left);
+        }
+    }
+    return p8_pair_finish<kBand>(s, st, r2, suspect);
+}
+#undef CTC_PAIR_ESCAPE
+
+// FAST generic-power DE of one sample (config 4's P = 2, 4, 16, ...): trig-free complex binary powers
+//   (z + i w)^P = r^P (cos P.theta + i sin P.theta),   ((x + i y)/w)^P = cos P.phi + i sin P.phi
+template <bool kBand>
+__device__ __forceinline__ float mandelbulb_de_fast_generic(const ShapeDev& s, float px, float py, float pz, bool& suspect) {
+    const uint32_t P = s.power;
     const float bail2 = s.bail2;
     float zx = px, zy = py, zz = pz;
-    float dr = 1.0f, r2;
-    uint32_t left = s.max_iters;                 // >= 1 (checked on the host, mandelbulb.rs:20)
-    do {
+    float dr = 1.0f, drmax = 1.0f, r2;
+    int logp = 0;
+    uint32_t left = s.max_iters;
+    for (;;) {
         const float z2 = zz * zz;
         const float w2 = fmaf(zx, zx, zy * zy);
         r2 = w2 + z2;
-        if (r2 > bail2) break;                   // r > bailout, on squares
-        if (kP8) {
-            // dr = 8 r^7 dr + 1
-            const float r6 = r2 * r2 * r2;
-            dr = fmaf(8.0f * (r6 * fast_sqrt(r2)), dr, 1.0f);
-            rotate_p8_fast(zx, zy, zz, z2, w2, px, py, pz, zx, zy, zz);
-        } else {
-            const float r = fast_sqrt(r2);
-            // generic P without trig: (z + i w)^P = r^P (cos P.theta + i sin P.theta),
-            // ((x + i y)/w)^P = cos P.phi + i sin P.phi
-            float rp1 = 1.0f;                       // r^(P-1)
-            { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
-            dr = fmaf((float)P * rp1, dr, 1.0f);
-            const float iw = fast_rsqrt(fmaxf(w2, 1e-36f));
-            const float w = w2 * iw;
-            float ct, st, cp, sp;
-            cpow(zz, w, P, ct, st);                 // r^P cos(P theta), r^P sin(P theta)
-            cpow(zx * iw, zy * iw, P, cp, sp);      // cos(P phi), sin(P phi)
-            zx = fmaf(st, cp, px); zy = fmaf(st, sp, py); zz = ct + pz;
+        if (r2 > bail2) {
+            suspect = fast_suspect_escaped<kBand>(s, drmax, logp);
+            return de_fast_epilogue(r2, dr);
         }
-    } while (--left);
-    // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
-    return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
-}
-
-// FAST power-8 DE for a sample of a lattice COLUMN: K1 walks 32 z-samples with (px, py) fixed, so the
-// first iteration's azimuth factors (c8, s8h), w and w2 are computed once per column and only the
-// elevation part of the first step is per sample.  Caller guarantees (px, py) != (0, 0).
-__device__ __forceinline__ float mandelbulb_de_fast_p8_column(const ShapeDev& s, float px, float py, float pz,
-                                                              float w2c, float wc, float c8, float s8h) {
-    const float bail2 = s.bail2;
-    float dr = 1.0f;
-    float r2 = fmaf(pz, pz, w2c);
-    if (!(r2 > bail2)) {
-        const float z2 = pz * pz;
-        const float r6 = r2 * r2 * r2;
-        dr = fmaf(8.0f, r6 * fast_sqrt(r2), 1.0f);           // 8 r^7 * 1 + 1
-        float A, Zh;
-        p8_elevation(pz, z2, wc, w2c, A, Zh);
-        float zx = fmaf(A, c8, px), zy = fmaf(2.0f * A, s8h, py), zz = fmaf(2.0f, Zh, pz);
-        for (uint32_t left = s.max_iters - 1u; left; --left) {
-            const float zz2 = zz * zz;
-            const float w2 = fmaf(zx, zx, zy * zy);
-            r2 = w2 + zz2;
-            if (r2 > bail2) break;
-            const float q6 = r2 * r2 * r2;
-            dr = fmaf(8.0f * (q6 * fast_sqrt(r2)), dr, 1.0f);
-            rotate_p8_fast(zx, zy, zz, zz2, w2, px, py, pz, zx, zy, zz);
-        }
+        const float r = fast_sqrt(r2);
+        float rp1 = 1.0f;                       // r^(P-1)
+        { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
+        dr = fmaf((float)P * rp1, dr, 1.0f);
+        drmax = fmaxf(drmax, dr);
+        if (--left == 0u) break;
+        const float iw = fast_rsqrt(w2);
+        const float w = w2 * iw;
+        float ct, st, cp, sp;
+        cpow(zz, w, P, ct, st);                 // r^P cos(P theta), r^P sin(P theta)
+        cpow(zx * iw, zy * iw, P, cp, sp);      // cos(P phi), sin(P phi)
+        logp += polar_stretch_log(st, iw, rp1);      // azimuthal stretch P |r^P sin| / w against P r^(P-1)
+        zx = fmaf(st, cp, px); zy = fmaf(st, sp, py); zz = ct + pz;
     }
-    return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
+    suspect = fast_suspect_inside<kBand>(s, r2, drmax, logp);
+    return de_fast_epilogue(r2, dr);
 }
 
 // Sphere::min_distance_from (sphere.rs:33-35); cgmath magnitude = sqrt((x*x+y*y)+z*z)
@@ -422,10 +685,25 @@ __device__ __forceinline__ float sphere_de(const ShapeDev& s, float px, float py
 // Shape dispatch.  kVariant: 0 = Mandelbulb P=8, 1 = Mandelbulb generic P, 2 = Sphere.
 enum : int { kVarP8 = 0, kVarGeneric = 1, kVarSphere = 2 };
 
-template <bool kFast, int kVariant, bool kCheckAxis = true>
+// The exact evaluation as an out-of-line call: the fallback of suspect fast results (rare).
+template <bool kP8>
+__device__ __noinline__ float mandelbulb_de_exact_cold(const ShapeDev& s, float px, float py, float pz) {
+    return mandelbulb_de_exact<kP8>(s, px, py, pz);
+}
+
+// One sample.  In fast mode a result whose sign cannot be trusted (kBand = true) or that touched the
+// z axis / went NaN (always) is replaced by the exact evaluation, so the SIGN FIELD of fast mode is
+// the exact mode's (for P = 8: the reference's) and fast mode differs in value only.
+template <bool kFast, int kVariant, bool kBand = true>
 __device__ __forceinline__ float shape_de(const ShapeDev& s, float px, float py, float pz) {
     if (kVariant == kVarSphere) return sphere_de(s, px, py, pz);
-    if (kFast) return mandelbulb_de_fast<kVariant == kVarP8, kCheckAxis>(s, px, py, pz);
+    if (kFast) {
+        bool suspect;
+        float d = (kVariant == kVarP8) ? mandelbulb_de_fast_p8<kBand>(s, px, py, pz, suspect)
+                                       : mandelbulb_de_fast_generic<kBand>(s, px, py, pz, suspect);
+        if (suspect) d = mandelbulb_de_exact_cold<kVariant == kVarP8>(s, px, py, pz);
+        return d;
+    }
     return mandelbulb_de_exact<kVariant == kVarP8>(s, px, py, pz);
 }
 

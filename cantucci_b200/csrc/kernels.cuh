@@ -45,6 +45,8 @@ struct MeshState {
     unsigned int panic_span;        // min global span index whose lerp factor left [0,1]; 0xFFFFFFFF = none
     unsigned int wire_overflow;     // 1 = a vertex id did not fit the packed 16-bit quad record
     unsigned int pad_;
+    unsigned long long suspects;    // fast mode: samples re-evaluated with the exact arithmetic (all groups)
+    unsigned long long sign_fixups; // ... of which the sign differed from the fast evaluation's
 };
 
 constexpr int kThreads = 256;
@@ -105,25 +107,38 @@ __device__ __forceinline__ void decode_sample(uint32_t i, uint32_t R, uint32_t l
 //
 // Blocks [0, core_blocks), R >= 32: a warp owns a 2x4xL block of the R^3 core
 // (or a 1x8xL / 8x1xL block of the x = R / y = R face; L = 64 for R >= 64, else 32)
-// and walks it in L/4 steps of one 32-sample brick, so iteration counts inside a warp stay coherent, the
-// per-warp set-up (decode, geometry load, x/y position) is paid once per 256
-// samples, and the 8 ballots assemble the 8 row words of the block's sign bits
-// without shared memory.  Remaining blocks: the z = R face, edges and corner
-// (and everything when R < 32), one thread per sample.
+// and walks it in L/8 steps of one 2x4x8 brick.  Every lane evaluates TWO samples
+// of its lattice column per step (z and z + 4) in packed FP32 (FFMA2/FMUL2/FADD2),
+// so iteration counts inside a warp stay coherent, the per-warp set-up (decode,
+// geometry load, x/y position, the first iteration's azimuth factors) is paid once
+// per 512 samples, and the ballots assemble the row words of the block's sign bits
+// without shared memory.  Remaining blocks: the z = R face, edges and corner (and
+// everything when R < 32), one thread per sample.
+//
+// Fast mode is SIGN-EXACT: a sample whose sign cannot be trusted (fast_suspect_*,
+// de_device.cuh) is appended to the group's suspect list and re-evaluated with
+// the exact arithmetic by fixup_suspects_kernel, which also repairs the plane.
 // ---------------------------------------------------------------------------
+struct SuspectList {
+    uint2* entries;          // (span in group, sample index j | fast sign << 31); j < 1025^3 < 2^31
+    unsigned int* count;     // appended so far (may exceed cap: the overflow was evaluated in place)
+    uint32_t cap;
+};
+
 template <bool kFast, int kVariant>
-__global__ void __launch_bounds__(kThreads)
-sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r, float dvz4,
+__global__ void __launch_bounds__(kThreads, kFast && kVariant == kVarP8 ? 3 : 1)
+sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r, float dvz8,
                     float* __restrict__ grids, size_t grid_stride,
                     uint32_t* __restrict__ sign_bits, uint32_t sign_stride /* words per span, 0 = no plane */,
-                    uint32_t core_blocks, uint32_t lgw /* log2(32-sample words per warp walk): 0 or 1 */) {
+                    uint32_t core_blocks, uint32_t lgw /* log2(32-sample words per warp walk): 0 or 1 */,
+                    SuspectList sl) {
     const uint32_t n = R + 1u;
     const SpanGeom g = geom[blockIdx.y];
     float* __restrict__ grid = grids + (size_t)blockIdx.y * grid_stride;
     uint32_t* __restrict__ plane = sign_bits + (size_t)blockIdx.y * sign_stride;
     if (blockIdx.x < core_blocks) {
         // warp-blocks of L = 32 << lgw z-samples: [0, R^3/(8L)) core 2x4xL; then R^2/(8L) blocks 1x8xL of
-        // the x = R face; then R^2/(8L) blocks 8x1xL of the y = R face.  Each is walked in L/4 brick steps.
+        // the x = R face; then R^2/(8L) blocks 8x1xL of the y = R face.  Each is walked in L/8 brick steps.
         const uint32_t lane = threadIdx.x & 31u;
         const uint32_t wb = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
         const uint32_t lgL = 5u + lgw;
@@ -140,11 +155,14 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
             const uint32_t t = ((ff >> (lg - lgL)) << 3) | (lane >> 2);
             if (f < n_face) { x = R; y = t; } else { x = t; y = R; }
         }
-        const uint32_t z = (zb << lgL) | (lane & 3u);
+        const uint32_t z = (zb << lgL) | (lane & 3u);   // this lane's samples of a step: z and z + 4
         // v = (x,y,z) as f32 / R  (exact: R is a power of two);  p = start + across * v  (buffer.rs:79-80)
         const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
         const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
-        float vz = __fmul_rn((float)z, inv_r);          // exact increments: multiples of 1/R in [0,1]
+        // exact increments: multiples of 1/R in [0,1].  The position arithmetic stays SCALAR: ptxas fuses a
+        // packed mul.rn.f32x2 + add.rn.f32x2 pair into one FFMA2 (even with -fmad=false), which would change
+        // the sample positions by an ulp (buffer.rs:79-80 is a multiply, then an add).
+        float vza = __fmul_rn((float)z, inv_r), vzb = __fmul_rn((float)(z + 4u), inv_r);
         float* out = grid + ((size_t)x * n + y) * n + z;                         // util/grid.rs:45-48
         uint32_t row_shift = (lane >> 2) << 2;          // this lane's row (xl,yl) nibble in a brick ballot
         asm volatile("" : "+r"(row_shift));             // keep it in a register (no S2R re-read per step)
@@ -153,20 +171,27 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         const bool writer = sign_stride != 0u && (lane & 3u) == 0u;
         // the on-axis special case of the column paths is tested once per warp, not once per sample
         const bool any_axis = (kFast || kVariant == kVarP8) && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
-        // 8 steps fill one 32-bit row word of the sign plane, which is then OR-ed in (two atomics)
-#define CTC_K1_STEPS(DE_EXPR)                                                                      \
+        // 4 steps fill one 32-bit row word of the sign plane, which is then OR-ed in (two atomics).
+        // DE_PAIR sets `float2 d` from (px, py, pz.x) and (px, py, pz.y).
+#define CTC_K1_STEPS(...)                                                                          \
         _Pragma("unroll 1")                                                                        \
         for (uint32_t h = 0; h < (1u << lgw); ++h) {                                               \
             uint32_t word = 0;                                                                     \
             _Pragma("unroll 1")                                                                    \
-            for (int j = 0; j < 8; ++j) {                                                          \
-                const float pz = __fadd_rn(gs2, __fmul_rn(ga2, vz));                               \
-                const float d = DE_EXPR;                                                           \
-                *out = d;                                                                          \
-                out += 4;                                                                          \
-                const uint32_t b = __ballot_sync(0xffffffffu, __float_as_uint(d) >> 31);           \
-                word = __funnelshift_r(word, b >> row_shift, 4);   /* nibble j -> bits [4j, 4j+4) */ \
-                vz = __fadd_rn(vz, dvz4);                                                          \
+            for (int j = 0; j < 4; ++j) {                                                          \
+                const float2 pz = make_float2(__fadd_rn(gs2, __fmul_rn(ga2, vza)),                 \
+                                              __fadd_rn(gs2, __fmul_rn(ga2, vzb)));                \
+                float2 d;                                                                          \
+                __VA_ARGS__                                                                        \
+                out[0] = d.x;                                                                      \
+                out[4] = d.y;                                                                      \
+                out += 8;                                                                          \
+                const uint32_t ba = __ballot_sync(0xffffffffu, __float_as_uint(d.x) >> 31);        \
+                const uint32_t bb = __ballot_sync(0xffffffffu, __float_as_uint(d.y) >> 31);        \
+                const uint32_t byte = ((ba >> row_shift) & 15u) | (((bb >> row_shift) & 15u) << 4); \
+                word = (word >> 8) | (byte << 24);                   /* byte j -> bits [8j, 8j+8) */ \
+                vza = __fadd_rn(vza, dvz8);                                                        \
+                vzb = __fadd_rn(vzb, dvz8);                                                        \
             }                                                                                      \
             if (writer && word != 0u) {                                                            \
                 const uint32_t j0 = j_row + (h << 5);                                              \
@@ -176,20 +201,38 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
             }                                                                                      \
         }
         if (any_axis) {
-            CTC_K1_STEPS((shape_de<kFast, kVariant, true>(sh, px, py, pz)))
+            CTC_K1_STEPS(d.x = shape_de<kFast, kVariant>(sh, px, py, pz.x); d.y = shape_de<kFast, kVariant>(sh, px, py, pz.y);)
         } else if (kFast && kVariant == kVarP8) {
             // (px, py) is fixed along the walk: hoist the first iteration's azimuth factors
-            const float w2c = fmaf(px, px, py * py);
-            float iw, c8, s8h;
-            p8_azimuth(px, py, w2c, iw, c8, s8h);
-            const float wc = w2c * iw;
-            CTC_K1_STEPS((mandelbulb_de_fast_p8_column(sh, px, py, pz, w2c, wc, c8, s8h)))
+            const ColumnFastP8 col = column_fast_p8(px, py);
+            const uint32_t lt = (1u << lane) - 1u;
+            CTC_K1_STEPS(
+                uint32_t susp;
+                d = mandelbulb_de_fast_p8_column_pair<true>(sh, px, py, pz, col, susp);
+                const uint32_t ma = __ballot_sync(0xffffffffu, susp & 1u);
+                const uint32_t mb = __ballot_sync(0xffffffffu, susp & 2u);
+                if (ma | mb) {      /* rare: queue the suspects for the exact re-evaluation */
+                    uint32_t base = 0;
+                    if (lane == 0u) base = atomicAdd(sl.count, (unsigned int)(__popc(ma) + __popc(mb)));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const uint32_t jj = (uint32_t)(out - grid);
+                    if (susp & 1u) {
+                        const uint32_t slot = base + __popc(ma & lt);
+                        if (slot < sl.cap) sl.entries[slot] = make_uint2(blockIdx.y, jj | (__float_as_uint(d.x) & 0x80000000u));
+                        else d.x = mandelbulb_de_exact_cold<true>(sh, px, py, pz.x);
+                    }
+                    if (susp & 2u) {
+                        const uint32_t slot = base + __popc(ma) + __popc(mb & lt);
+                        if (slot < sl.cap) sl.entries[slot] = make_uint2(blockIdx.y, (jj + 4u) | (__float_as_uint(d.y) & 0x80000000u));
+                        else d.y = mandelbulb_de_exact_cold<true>(sh, px, py, pz.y);
+                    }
+                })
         } else if (!kFast && kVariant == kVarP8) {
             // exact arithmetic: hoist the x/y-only sub-expressions of the first iteration (bit-identical CSE)
             const ColumnExactP8 col = column_exact_p8(px, py);
-            CTC_K1_STEPS((mandelbulb_de_exact_p8_column(sh, px, py, pz, col)))
+            CTC_K1_STEPS(d.x = mandelbulb_de_exact_p8_column(sh, px, py, pz.x, col); d.y = mandelbulb_de_exact_p8_column(sh, px, py, pz.y, col);)
         } else {
-            CTC_K1_STEPS((shape_de<kFast, kVariant, false>(sh, px, py, pz)))
+            CTC_K1_STEPS(d.x = shape_de<kFast, kVariant>(sh, px, py, pz.x); d.y = shape_de<kFast, kVariant>(sh, px, py, pz.y);)
         }
 #undef CTC_K1_STEPS
         return;
@@ -216,10 +259,47 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
     const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
     const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
     const float pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));
-    const float d = shape_de<kFast, kVariant>(sh, px, py, pz);
+    const float d = shape_de<kFast, kVariant>(sh, px, py, pz);      // fast mode: suspects re-evaluated in place
     const uint32_t j = (x * n + y) * n + z;
     grid[j] = d;
     if (sign_stride != 0u && (__float_as_uint(d) >> 31)) atomicOr(&plane[j >> 5], 1u << (j & 31u));
+}
+
+// Exact re-evaluation of the suspects K1 queued (fast mode): overwrites the sample and, where the
+// sign changes, flips its bit of the plane.  Persistent grid-stride loop (the count lives on the device).
+// The entry carries the fast evaluation's sign, so the kernel only WRITES the grid (a scattered read of
+// the 4-byte sample, one DRAM sector and often a TLB miss per suspect, was 20x the cost of the arithmetic).
+template <int kVariant>
+__global__ void __launch_bounds__(kThreads)
+fixup_suspects_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, float inv_r,
+                      float* __restrict__ grids, size_t grid_stride, uint32_t* __restrict__ sign_bits, uint32_t sign_stride,
+                      SuspectList sl, MeshState* __restrict__ st /* may be NULL */) {
+    const uint32_t n = R + 1u;
+    const uint32_t total = *sl.count;
+    const uint32_t cnt = min(total, sl.cap);
+    uint32_t flips = 0;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) {
+        const uint2 e = sl.entries[i];
+        const uint32_t j = e.y & 0x7fffffffu, was = e.y >> 31;
+        const uint32_t z = j % n, xy = j / n, y = xy % n, x = xy / n;
+        const SpanGeom g = geom[e.x];
+        const float px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
+        const float py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
+        const float pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));
+        const float d = mandelbulb_de_exact<kVariant == kVarP8>(sh, px, py, pz);
+        grids[(size_t)e.x * grid_stride + j] = d;
+        const uint32_t is = __float_as_uint(d) >> 31;
+        if (was != is) {
+            ++flips;
+            if (sign_stride != 0u) atomicXor(&sign_bits[(size_t)e.x * sign_stride + (j >> 5)], 1u << (j & 31u));
+        }
+    }
+    if (st) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) flips += __shfl_xor_sync(0xffffffffu, flips, o);
+        if ((threadIdx.x & 31u) == 0u && flips) atomicAdd(&st->sign_fixups, (unsigned long long)flips);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st->suspects, (unsigned long long)total);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -456,7 +536,7 @@ apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_counts, const uint2
 // cells (the count lives on the device, no host sync).  One thread per vertex.
 // ---------------------------------------------------------------------------
 template <bool kFast, int kVariant>
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, 4)
 vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __restrict__ grids, size_t grid_stride,
               uint32_t R, uint32_t lg, const uint32_t* __restrict__ cell_of, uint32_t cell_cap, MeshState* st,
               uint32_t span0, float* __restrict__ out_v, unsigned long long vcap) {
@@ -522,22 +602,35 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
         const float qz = M::add(0.0f, M::div(sz_, fc));
 
         // dist_p and the un-normalised central differences (buffer.rs:254-265).
-        // unit_x() * d = (1*d, 0*d, 0*d): the zero products keep their sign.
-        float de[7];
+        // unit_x() * d = (1*d, 0*d, 0*d): the zero products keep their sign.  The reference multiplies
+        // the unit vector by +-delta.<axis>, so the two off-axis components are p + 0 * (+-delta.<axis>).
+        float ex[7], ey[7], ez[7], de[7];
+        ex[0] = qx; ey[0] = qy; ez[0] = qz;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const int axis = (k - 1) >> 1;                 // k=0: none
+        for (int k = 1; k < 7; ++k) {
+            const int axis = (k - 1) >> 1;
             const float sg = (k & 1) ? 1.0f : -1.0f;       // odd k: +delta, even k: -delta
-            float ex = qx, ey = qy, ez = qz;
-            if (k > 0) {
-                // the reference multiplies the unit vector by +-delta.<axis>, so the two
-                // off-axis components are p + 0 * (+-delta.<axis>)
-                const float da = sg * (axis == 0 ? g.delta[0] : axis == 1 ? g.delta[1] : g.delta[2]);
-                ex = M::add(qx, M::mul(axis == 0 ? 1.0f : 0.0f, da));
-                ey = M::add(qy, M::mul(axis == 1 ? 1.0f : 0.0f, da));
-                ez = M::add(qz, M::mul(axis == 2 ? 1.0f : 0.0f, da));
+            const float da = sg * (axis == 0 ? g.delta[0] : axis == 1 ? g.delta[1] : g.delta[2]);
+            ex[k] = M::add(qx, M::mul(axis == 0 ? 1.0f : 0.0f, da));
+            ey[k] = M::add(qy, M::mul(axis == 1 ? 1.0f : 0.0f, da));
+            ez[k] = M::add(qz, M::mul(axis == 2 ? 1.0f : 0.0f, da));
+        }
+        if (kFast && kVariant == kVarP8) {
+            // the +-delta evaluations of an axis go through the packed FP32 path as one pair; values only
+            // (normals, distance_from_surface), so only the z-axis / NaN rule sends a point to the exact path
+            de[0] = shape_de<true, kVarP8, false>(sh, ex[0], ey[0], ez[0]);
+#pragma unroll
+            for (int k = 1; k < 7; k += 2) {
+                uint32_t susp;
+                const float2 d2 = mandelbulb_de_fast_p8_pair<false>(sh, make_float2(ex[k], ex[k + 1]), make_float2(ey[k], ey[k + 1]),
+                                                                    make_float2(ez[k], ez[k + 1]), susp);
+                de[k] = d2.x; de[k + 1] = d2.y;
+                if (susp & 1u) de[k] = mandelbulb_de_exact_cold<true>(sh, ex[k], ey[k], ez[k]);
+                if (susp & 2u) de[k + 1] = mandelbulb_de_exact_cold<true>(sh, ex[k + 1], ey[k + 1], ez[k + 1]);
             }
-            de[k] = shape_de<kFast, kVariant>(sh, ex, ey, ez);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) de[k] = shape_de<kFast, kVariant, false>(sh, ex[k], ey[k], ez[k]);
         }
         const float nx = M::sub(de[1], de[2]), ny = M::sub(de[3], de[4]), nz = M::sub(de[5], de[6]);
         // cgmath normalize: v * (1 / sqrt((x*x + y*y) + z*z))
@@ -705,6 +798,93 @@ iteration_stats_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t 
     }
 }
 
+// Calibration of the sign-trust band (fast_suspect_*, de_device.cuh): every sample of the span batch is
+// evaluated by the fast path (raw, no repair) AND by the exact path.  out[] (unsigned long long):
+//   [0] samples                      [1] raw sign mismatches fast vs exact
+//   [2] mismatches with an iterate on the z axis (accumulated polar stretch >= 2^10)
+//   [3] samples not escaped in both  [4] samples whose escape status differs
+//   [5] max |r2_fast - r2_exact| / max dr over [3], as float bits    [6] the same over (max dr * polar stretch)
+//   [7] mismatches where the fast path escaped
+//   [8 + 4q ..] for q = 0..23, kappa = 2^-(8+q), axis rule applied first:
+//        suspects / uncovered mismatches with the band kappa * max dr, then with kappa * max dr * polar stretch
+//   [kProbeWords ..] up to kProbeDump records of 12 floats: mismatches the band 2^-17 * max dr * stretch misses
+constexpr int kProbeKappas = 24;
+constexpr int kProbeWords = 8 + 4 * kProbeKappas;
+constexpr int kProbeDump = 64;
+
+__global__ void __launch_bounds__(kThreads)
+fast_sign_probe_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r,
+                       unsigned long long* __restrict__ out, float* __restrict__ dump, unsigned int* __restrict__ dump_count) {
+    __shared__ unsigned int acc[kProbeWords];
+    for (int i = threadIdx.x; i < kProbeWords; i += kThreads) acc[i] = 0u;
+    __syncthreads();
+    const uint32_t n = R + 1u, n3 = n * n * n;
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    const bool live = i < n3;
+    bool mism = false, axis = false, esc_e = false, both_in = false;
+    FastInfo fi{1.0f, 1.0f, 1.0f, 1.0f, 1u, 1.0f, 1.0f};
+    float e_max = 0.0f, e_pol = 0.0f, px = 0.f, py = 0.f, pz = 0.f, re = 0.f, df = 0.f, dx = 0.f;
+    if (live) {
+        uint32_t x, y, z;
+        decode_sample(i, R, lg, x, y, z);
+        const SpanGeom g = geom[blockIdx.y];
+        px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
+        py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
+        pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));
+        df = mandelbulb_de_fast_p8_probe(sh, px, py, pz, fi);
+        uint32_t it;
+        dx = mandelbulb_de_exact<true>(sh, px, py, pz, &it, &re);
+        esc_e = it < sh.max_iters;
+        mism = (__float_as_uint(df) >> 31) != (__float_as_uint(dx) >> 31);
+        axis = !(fi.polar < 1024.0f);
+        both_in = !fi.escaped && !esc_e;
+        if (both_in && !axis) {
+            const float err = fabsf(fi.r2 - re * re);
+            if (err == err) { e_max = err / fi.drmax; e_pol = err / (fi.drmax * fi.polar); }
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+#define CTC_PROBE_COUNT(K, COND)                                                         \
+    { const uint32_t b_ = __ballot_sync(0xffffffffu, live && (COND));                    \
+      if (lane == 0u && b_) atomicAdd(&acc[K], (unsigned int)__popc(b_)); }
+    CTC_PROBE_COUNT(0, true)
+    CTC_PROBE_COUNT(1, mism)
+    CTC_PROBE_COUNT(2, mism && axis)
+    CTC_PROBE_COUNT(3, both_in)
+    CTC_PROBE_COUNT(4, (fi.escaped != 0u) != esc_e)
+    CTC_PROBE_COUNT(7, mism && fi.escaped)
+    atomicMax(&acc[5], __float_as_uint(e_max));
+    atomicMax(&acc[6], __float_as_uint(e_pol));
+    float kappa = 1.0f / 256.0f;
+    for (int q = 0; q < kProbeKappas; ++q, kappa *= 0.5f) {
+        bool s_max, s_pol;
+        if (fi.escaped) { s_max = axis || !(kappa * fi.drmax < 4.0f); s_pol = axis || !(kappa * fi.drmax * fi.polar < 4.0f); }
+        else {
+            s_max = axis || !(fabsf(fi.r2 - 1.0f) > kappa * fi.drmax);
+            s_pol = axis || !(fabsf(fi.r2 - 1.0f) > kappa * fi.drmax * fi.polar);
+        }
+        CTC_PROBE_COUNT(8 + 4 * q, s_max)
+        CTC_PROBE_COUNT(9 + 4 * q, mism && !s_max)
+        CTC_PROBE_COUNT(10 + 4 * q, s_pol)
+        CTC_PROBE_COUNT(11 + 4 * q, mism && !s_pol)
+        if (q == 9 && live && mism && !s_pol) {
+            const unsigned int slot = atomicAdd(dump_count, 1u);
+            if (slot < (unsigned)kProbeDump) {
+                float* o = dump + 12 * slot;
+                o[0] = px; o[1] = py; o[2] = pz; o[3] = fi.r2; o[4] = re * re; o[5] = fi.dr; o[6] = fi.drmax;
+                o[7] = fi.wmin; o[8] = fi.polar; o[9] = fi.wrmin; o[10] = df; o[11] = dx;
+            }
+        }
+    }
+#undef CTC_PROBE_COUNT
+    __syncthreads();
+    for (int k = threadIdx.x; k < kProbeWords; k += kThreads) {
+        const unsigned long long v = acc[k];
+        if (v == 0ull) continue;
+        if (k == 5 || k == 6) atomicMax(&out[k], v); else atomicAdd(&out[k], v);
+    }
+}
+
 // Dependent-free FFMA streams: the sustained FP32 FMA rate of this GPU at its running clock
 // (the denominator SURVEY.md 8d asks to be reported beside the nominal SMs*128*2*clock).
 __global__ void __launch_bounds__(kThreads)
@@ -726,7 +906,7 @@ fma_peak_kernel(float* __restrict__ out, uint32_t iters) {
 __global__ void reset_state_kernel(MeshState* st) {
     st->total_v = 0; st->total_q = 0; st->group_base_v = 0; st->group_base_q = 0;
     st->group_v = 0; st->group_q = 0; st->overflow = 0; st->panic_span = 0xFFFFFFFFu;
-    st->wire_overflow = 0; st->pad_ = 0;
+    st->wire_overflow = 0; st->pad_ = 0; st->suspects = 0; st->sign_fixups = 0;
 }
 
 }  // namespace ctc

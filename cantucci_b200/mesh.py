@@ -82,6 +82,20 @@ def sample_grids(spans, shape: Shape, resolution: int, ctx: _lib.Context | None 
     return out
 
 
+def sample_signs(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = None) -> np.ndarray:
+    """Sign bit-planes of the spans' sample grids: [nspans, ((R+1)^3 + 31) // 32] u32, bit j of a plane =
+    not is_sign_positive(grid[j]) (parity aid: the mesher's topology is a function of these bits)."""
+    ctx = ctx or _lib.default_context()
+    arr = spans_array(spans)
+    _check_args(arr, resolution)
+    words = ((resolution + 1) ** 3 + 31) // 32
+    out = np.zeros((arr.shape[0], words), dtype=np.uint32)
+    sh = shape._ctc_shape()
+    ctx.check(_lib.lib().ctc_sample_signs(ctx.handle, C.byref(sh), arr.ctypes.data, arr.shape[0], resolution,
+                                          out.ctypes.data))
+    return out
+
+
 def generate_for_boxes(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = None,
                        vcap: int | None = None, icap: int | None = None, out_v: np.ndarray | None = None,
                        out_i: np.ndarray | None = None):

@@ -218,6 +218,28 @@ CTC_API int ctc_host_unregister(ctc_ctx *ctx, void *ptr);
  * flop count flops(sample) = 75 k + 6 [bailed] + 10. Host pointers; synchronous. */
 CTC_API int ctc_iteration_stats(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
                                 uint32_t resolution, uint64_t out[3]);
+/* ---- fast mode's sign repair (CTC_MATH_FAST) ----------------------------------
+ * Fast mode is SIGN-EXACT: a sample whose sign the fast arithmetic cannot guarantee (its last radius
+ * is within kappa * max dr * polar stretch of 1, an iterate touched the z axis, or anything went NaN)
+ * is re-evaluated with the exact arithmetic, so that the inside/outside classification -- and with it
+ * every index buffer -- equals exact mode's (for power 8: the reference's).
+ * ctc_ctx_set_fast_band overrides the calibrated band (0 = default); ctc_mesh_fixups reports, for the
+ * last mesh call whose result was fetched, how many samples were re-evaluated and how many of those
+ * changed sign. */
+CTC_API int ctc_ctx_set_fast_band(ctc_ctx *ctx, float kappa);
+CTC_API int ctc_mesh_fixups(ctc_ctx *ctx, uint64_t *suspects, uint64_t *sign_fixups);
+/* Parity aid: the sign bit-planes of the spans' sample grids as pass 1 produces them (fast mode: after
+ * the sign repair).  planes: nspans x ((R+1)^3 + 31) / 32 u32, HOST pointer; bit j of a span's plane is
+ * !f32::is_sign_positive(grid[j]), j = x*(R+1)^2 + y*(R+1) + z -- everything the mesher's topology
+ * depends on (src/mesh/buffer.rs:130-147, 299-350).  Synchronous. */
+CTC_API int ctc_sample_signs(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                             uint32_t resolution, uint32_t *planes);
+/* Calibration aid: evaluates every sample of the spans' lattices with the raw fast path AND the exact
+ * path and counts sign mismatches, suspects and uncovered mismatches for kappa = 2^-8 .. 2^-31
+ * (layout: csrc/kernels.cuh, fast_sign_probe_kernel; out_words >= 489).  Power 8 only. */
+CTC_API int ctc_fast_sign_probe(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                                uint32_t resolution, uint64_t *out, size_t out_words);
+
 /* Sustained FP32 FMA rate of the device in TFLOP/s (FMA = 2 flops), measured
  * with dependent-free FFMA streams on every SM. */
 CTC_API int ctc_fp32_peak_probe(ctc_ctx *ctx, double *tflops, int *num_sms);

@@ -390,7 +390,16 @@ static void ipush6(ibuf *b, const uint32_t x[6]) {
     b->n += 6;
 }
 
+/* plane (may be NULL): the sign bit-plane of the sample grid, bit j of word j/32 =
+ * !f32::is_sign_positive(dists[j]), j = x*n^2 + y*n + z; (n^3 + 31)/32 words.  Checker output for the
+ * parity gate (sign mismatches of the CUDA path are counted against it). */
+static int generate_for_box_impl(const orc_shape *s, const orc_span *span_in, uint32_t R, orc_mesh *out, uint32_t *plane);
+
 int orc_generate_for_box(const orc_shape *s, const orc_span *span_in, uint32_t R, orc_mesh *out) {
+    return generate_for_box_impl(s, span_in, R, out, NULL);
+}
+
+static int generate_for_box_impl(const orc_shape *s, const orc_span *span_in, uint32_t R, orc_mesh *out, uint32_t *plane) {
     memset(out, 0, sizeof *out);
     if (check_args(span_in, R)) return 1;
 
@@ -403,6 +412,12 @@ int orc_generate_for_box(const orc_shape *s, const orc_span *span_in, uint32_t R
     const uint32_t n = R + 1;
     float *dists = malloc((size_t)n * n * n * sizeof(float));
     sample_grid(s, &span, R, dists, NULL, NULL);
+    if (plane) {
+        const size_t n3 = (size_t)n * n * n;
+        memset(plane, 0, ((n3 + 31) / 32) * sizeof(uint32_t));
+        for (size_t j = 0; j < n3; j++)
+            if (!sign_positive(dists[j])) plane[j >> 5] |= 1u << (j & 31);
+    }
 
     const double before_second = now_s();
 
@@ -565,6 +580,7 @@ void orc_mesh_free(orc_mesh *m) {
 typedef struct {
     const orc_shape *shape; const orc_span *spans; size_t nspans; uint32_t R;
     orc_mesh *meshes; atomic_size_t next; int grids_only; double checksum; pthread_mutex_t mu;
+    uint32_t *planes; size_t plane_words;
 } pool_job;
 
 static void *pool_worker(void *arg) {
@@ -580,7 +596,8 @@ static void *pool_worker(void *arg) {
             size_t n = (size_t)(j->R + 1) * (j->R + 1) * (j->R + 1);
             for (size_t k = 0; k < n; k += 97) if (grid[k] == grid[k]) local += grid[k];
         } else {
-            orc_generate_for_box(j->shape, &j->spans[i], j->R, &j->meshes[i]);
+            generate_for_box_impl(j->shape, &j->spans[i], j->R, &j->meshes[i],
+                                  j->planes ? j->planes + i * j->plane_words : NULL);
         }
     }
     free(grid);
@@ -605,6 +622,14 @@ static double run_pool(pool_job *j, int nthreads) {
 double orc_generate_for_boxes_mt(const orc_shape *s, const orc_span *spans, size_t nspans,
                                  uint32_t resolution, int nthreads, orc_mesh *meshes) {
     pool_job j = { .shape = s, .spans = spans, .nspans = nspans, .R = resolution, .meshes = meshes };
+    return run_pool(&j, nthreads);
+}
+
+double orc_generate_for_boxes_signs_mt(const orc_shape *s, const orc_span *spans, size_t nspans,
+                                       uint32_t resolution, int nthreads, orc_mesh *meshes, uint32_t *planes) {
+    const size_t n = (size_t)resolution + 1;
+    pool_job j = { .shape = s, .spans = spans, .nspans = nspans, .R = resolution, .meshes = meshes,
+                   .planes = planes, .plane_words = (n * n * n + 31) / 32 };
     return run_pool(&j, nthreads);
 }
 

@@ -94,6 +94,10 @@ void orc_mesh_free(orc_mesh *m);
  * nthreads workers.  meshes[nspans] is filled; returns wall seconds. */
 double orc_generate_for_boxes_mt(const orc_shape *s, const orc_span *spans, size_t nspans,
                                  uint32_t resolution, int nthreads, orc_mesh *meshes);
+/* Same, and also the sign bit-plane of every span's sample grid: planes[nspans][((R+1)^3 + 31) / 32],
+ * bit j = !is_sign_positive(dists[j]).  Used by the parity gate to count sign mismatches. */
+double orc_generate_for_boxes_signs_mt(const orc_shape *s, const orc_span *spans, size_t nspans,
+                                       uint32_t resolution, int nthreads, orc_mesh *meshes, uint32_t *planes);
 /* Same pool, pass 1 only (samples), results discarded except a checksum. */
 double orc_sample_grids_mt(const orc_shape *s, const orc_span *spans, size_t nspans,
                            uint32_t resolution, int nthreads, double *checksum);

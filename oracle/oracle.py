@@ -109,6 +109,9 @@ def lib() -> C.CDLL:
         L.orc_generate_for_boxes_mt.restype = C.c_double
         L.orc_generate_for_boxes_mt.argtypes = [C.POINTER(Shape), C.c_void_p, C.c_size_t, C.c_uint32,
                                                 C.c_int, C.c_void_p]
+        L.orc_generate_for_boxes_signs_mt.restype = C.c_double
+        L.orc_generate_for_boxes_signs_mt.argtypes = [C.POINTER(Shape), C.c_void_p, C.c_size_t, C.c_uint32,
+                                                      C.c_int, C.c_void_p, C.c_void_p]
         L.orc_sample_grids_mt.restype = C.c_double
         L.orc_sample_grids_mt.argtypes = [C.POINTER(Shape), C.c_void_p, C.c_size_t, C.c_uint32, C.c_int,
                                           C.POINTER(C.c_double)]
@@ -257,6 +260,38 @@ def generate_for_boxes_mt(shape: Shape, spans, resolution: int, nthreads: int | 
         out.append(_mesh_out(meshes[k]))
         lib().orc_mesh_free(C.byref(meshes[k]))
     return out, secs
+
+
+def generate_for_boxes_flat_mt(shape: Shape, spans, resolution: int, nthreads: int | None = None, signs: bool = True):
+    """Thread-pool run returning FLAT arrays (the parity gate's checker): vertices [V] VERTEX_DTYPE,
+    indices [I] u32, v_off / i_off [n+1] (spans that panicked contribute nothing and are listed in
+    `panicked`), the sign bit-planes [n, words] u32 (or None) and the wall seconds of the pool."""
+    arr = spans_to_array(spans)
+    n = arr.shape[0]
+    meshes = (Mesh * n)()
+    if nthreads is None:
+        nthreads = lib().orc_hardware_threads()
+    words = ((resolution + 1) ** 3 + 31) // 32
+    planes = np.zeros((n, words), dtype=np.uint32) if signs else None
+    secs = lib().orc_generate_for_boxes_signs_mt(C.byref(shape), arr.ctypes.data, n, resolution, nthreads,
+                                                 C.addressof(meshes), planes.ctypes.data if signs else None)
+    nv = np.array([m.n_vertices for m in meshes], dtype=np.int64)
+    ni = np.array([m.n_indices for m in meshes], dtype=np.int64)
+    v_off = np.concatenate([[0], np.cumsum(nv)])
+    i_off = np.concatenate([[0], np.cumsum(ni)])
+    v = np.empty(int(v_off[-1]), dtype=VERTEX_DTYPE)
+    i = np.empty(int(i_off[-1]), dtype=np.uint32)
+    panicked = []
+    for k in range(n):
+        m = meshes[k]
+        if m.panicked:
+            panicked.append(k)
+        if m.n_vertices:
+            C.memmove(v.ctypes.data + int(v_off[k]) * 28, m.vertices, int(m.n_vertices) * 28)
+        if m.n_indices:
+            C.memmove(i.ctypes.data + int(i_off[k]) * 4, m.indices, int(m.n_indices) * 4)
+        lib().orc_mesh_free(C.byref(meshes[k]))
+    return v, i, v_off, i_off, planes, panicked, secs
 
 
 def sample_grids_mt(shape: Shape, spans, resolution: int, nthreads: int | None = None):
