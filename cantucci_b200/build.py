@@ -40,6 +40,12 @@ def is_stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPS)
 
 
+def build_variant(out: str, defines: list[str]) -> str:
+    """An A/B build of the same library with extra -D flags (select it with CANTUCCI_B200_LIB)."""
+    subprocess.run([nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *SOURCES], check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB

@@ -504,88 +504,64 @@ __device__ __forceinline__ float mandelbulb_de_fast_p8_probe(const ShapeDev& s, 
     return de_fast_epilogue(r2, dr);
 }
 
-// Two samples per thread.  State of a pair evaluation: the live iterate, and the snapshot of
-// (r^2, dr, max dr, polar stretch) a half leaves behind when it escapes.  An escaped half is parked on
-// NaN (its `+ p` operand), so it never escapes again, and BOTH distances are computed once, in packed
-// form, after the loop: the escape path is a handful of moves.
-struct PairP8 {
-    float2 px, py, pz;        // the two sample points
-    float2 zx, zy, zz;        // current iterate
-    float2 dr, drmax;
-    int2 logp;                // accumulated polar stretch (log domain)
-    float2 r2s, drs, dms;     // snapshot at escape: r^2, dr, max dr
-    int2 lps;
-    uint32_t esc;             // bit k: half k escaped
-};
-
-#define CTC_PAIR_ESCAPE(H, BIT)                                                                  \
+// Two samples per thread: the iteration loop shared by the column form (K1) and the point form (E3).
+// On entry (zx, zy, zz) hold the current iterate of both halves, `left` >= 1 radius tests remain.
+// A half that escapes gets its distance at once and is parked on NaN (its `+ p.z` operand), so it
+// neither escapes again nor disturbs the other half; (px, py) stay broadcast scalars when the halves
+// share a lattice column.  (A variant that snapshots the escaping half and computes both distances in
+// packed form after the loop measured 10 % slower: the extra live registers cost more moves than the
+// duplicated epilogue costs instructions.)
+#define CTC_PAIR_ESCAPE_IMM(H, BIT)                                                              \
     if (r2.H > bail2) {                                                                          \
-        st.r2s.H = r2.H; st.drs.H = st.dr.H; st.dms.H = st.drmax.H; st.lps.H = st.logp.H;        \
-        st.esc |= BIT;                                                                           \
-        st.px.H = __int_as_float(0x7fffffff);                                                    \
+        d.H = de_fast_epilogue(r2.H, dr.H);                                                      \
+        if (fast_suspect_escaped<kBand>(s, drmax.H, logp.H)) suspect |= BIT;                     \
+        done |= BIT;                                                                             \
+        pz.H = __int_as_float(0x7fffffff);                                                       \
     }
 
-// Runs the remaining iterations.  On entry (zx, zy, zz) hold the current iterate of both halves and
-// `left` >= 1 radius tests remain.  Returns the last r^2 of the halves that did not escape.
-__device__ __forceinline__ float2 p8_pair_loop(PairP8& st, float bail2, uint32_t left) {
+template <bool kBand>
+__device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float2 py, float2 pz, float2 zx, float2 zy, float2 zz,
+                                             float2 dr, float2 drmax, int2 logp, uint32_t left, float2& d,
+                                             uint32_t done, uint32_t& suspect) {
     using L = Lanes<float2>;
+    const float bail2 = s.bail2;
     float2 r2;
+#pragma unroll 2
     for (;;) {
-        const float2 z2 = L::mul(st.zz, st.zz);
-        const float2 w2 = L::fma(st.zx, st.zx, L::mul(st.zy, st.zy));
+        const float2 z2 = L::mul(zz, zz);
+        const float2 w2 = L::fma(zx, zx, L::mul(zy, zy));
         r2 = L::add(w2, z2);
         if ((r2.x > bail2) | (r2.y > bail2)) {
-            CTC_PAIR_ESCAPE(x, 1u)
-            CTC_PAIR_ESCAPE(y, 2u)
-            if (st.esc == 3u) break;
+            CTC_PAIR_ESCAPE_IMM(x, 1u)
+            CTC_PAIR_ESCAPE_IMM(y, 2u)
+            if (done == 3u) return;
         }
         float2 r7, A, iw;
-        st.dr = p8_dr<float2>(r2, st.dr, r7);
-        st.drmax = L::vmax(st.drmax, st.dr);
+        dr = p8_dr<float2>(r2, dr, r7);
+        drmax = L::vmax(drmax, dr);
         if (--left == 0u) break;
-        p8_step<float2>(st.zx, st.zy, st.zz, z2, w2, st.px, st.py, st.pz, A, iw);
-        st.logp.x += polar_stretch_log(A.x, iw.x, r7.x);
-        st.logp.y += polar_stretch_log(A.y, iw.y, r7.y);
+        p8_step<float2>(zx, zy, zz, z2, w2, px, py, pz, A, iw);
+        logp.x += polar_stretch_log(A.x, iw.x, r7.x);
+        logp.y += polar_stretch_log(A.y, iw.y, r7.y);
     }
-    return r2;
-}
-
-// Both distances and the suspect bits from the final state (r2 = last r^2 of the non-escaped halves).
-template <bool kBand>
-__device__ __forceinline__ float2 p8_pair_finish(const ShapeDev& s, const PairP8& st, float2 r2, uint32_t& suspect) {
-    using L = Lanes<float2>;
-    const bool ea = st.esc & 1u, eb = st.esc & 2u;
-    const float2 R2 = make_float2(ea ? st.r2s.x : r2.x, eb ? st.r2s.y : r2.y);
-    const float2 DR = make_float2(ea ? st.drs.x : st.dr.x, eb ? st.drs.y : st.dr.y);
-    const float2 DM = make_float2(ea ? st.dms.x : st.drmax.x, eb ? st.dms.y : st.drmax.y);
-    const int lpa = ea ? st.lps.x : st.logp.x, lpb = eb ? st.lps.y : st.logp.y;
-    // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
-    const float2 lg = make_float2(fast_lg2(R2.x), fast_lg2(R2.y));
-    const float2 rc = make_float2(fast_rcp(DR.x), fast_rcp(DR.y));
-    const float2 d = L::mul(L::mul(L::mul(lg, L::bc(0.25f * 0.69314718056f)), L::sqrt(R2)), rc);
-    uint32_t su = (lpa >= kAxisLog ? 1u : 0u) | (lpb >= kAxisLog ? 2u : 0u);
-    if (kBand) {
-        const float2 bound = L::mul(L::mul(DM, L::bc(s.kappa)), make_float2(polar_factor(lpa), polar_factor(lpb)));
-        const float ma = ea ? 4.0f : fabsf(R2.x - 1.0f), mb = eb ? 4.0f : fabsf(R2.y - 1.0f);
-        if (!(ma > bound.x)) su |= 1u;
-        if (!(mb > bound.y)) su |= 2u;
-    } else {
-        if (!(R2.x == R2.x)) su |= 1u;
-        if (!(R2.y == R2.y)) su |= 2u;
+    if (!(done & 1u)) {
+        d.x = de_fast_epilogue(r2.x, dr.x);
+        if (fast_suspect_inside<kBand>(s, r2.x, drmax.x, logp.x)) suspect |= 1u;
     }
-    suspect = su;
-    return d;
+    if (!(done & 2u)) {
+        d.y = de_fast_epilogue(r2.y, dr.y);
+        if (fast_suspect_inside<kBand>(s, r2.y, drmax.y, logp.y)) suspect |= 2u;
+    }
 }
 
 // FAST power-8 DE of two arbitrary points.  Bit k of `suspect`: the result of half k needs the exact path.
 template <bool kBand>
 __device__ __forceinline__ float2 mandelbulb_de_fast_p8_pair(const ShapeDev& s, float2 px, float2 py, float2 pz, uint32_t& suspect) {
-    PairP8 st;
-    st.px = px; st.py = py; st.pz = pz; st.zx = px; st.zy = py; st.zz = pz;
-    st.dr = make_float2(1.0f, 1.0f); st.drmax = st.dr; st.logp = make_int2(0, 0);
-    st.r2s = st.dr; st.drs = st.dr; st.dms = st.dr; st.lps = st.logp; st.esc = 0u;
-    const float2 r2 = p8_pair_loop(st, s.bail2, s.max_iters);
-    return p8_pair_finish<kBand>(s, st, r2, suspect);
+    float2 d = make_float2(0.0f, 0.0f);
+    suspect = 0u;
+    p8_pair_loop<kBand>(s, px, py, pz, px, py, pz, make_float2(1.0f, 1.0f), make_float2(1.0f, 1.0f),
+                        make_int2(0, 0), s.max_iters, d, 0u, suspect);
+    return d;
 }
 
 // FAST power-8 DE along a lattice COLUMN: K1 walks z with (px, py) fixed, so the first iteration's
@@ -608,36 +584,38 @@ __device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeD
                                                                     const ColumnFastP8& c, uint32_t& suspect) {
     using L = Lanes<float2>;
     const float bail2 = s.bail2;
-    PairP8 st;
-    st.px = L::bc(px_); st.py = L::bc(py_); st.pz = pz;
-    st.dr = L::bc(1.0f); st.drmax = st.dr; st.logp = make_int2(0, 0);
-    st.r2s = st.dr; st.drs = st.dr; st.dms = st.dr; st.lps = st.logp; st.esc = 0u;
-    uint32_t left = s.max_iters;
+    const float2 px = L::bc(px_), py = L::bc(py_);
+    float2 d = make_float2(0.0f, 0.0f), dr = L::bc(1.0f), drmax = L::bc(1.0f);
+    uint32_t done = 0u, left = s.max_iters;
+    int2 logp = make_int2(0, 0);
+    suspect = 0u;
     const float2 z2 = L::mul(pz, pz);
     const float2 w2 = L::bc(c.w2);
     float2 r2 = L::add(w2, z2);
     if ((r2.x > bail2) | (r2.y > bail2)) {
-        CTC_PAIR_ESCAPE(x, 1u)
-        CTC_PAIR_ESCAPE(y, 2u)
+        CTC_PAIR_ESCAPE_IMM(x, 1u)
+        CTC_PAIR_ESCAPE_IMM(y, 2u)
+        if (done == 3u) return d;
     }
-    if (st.esc != 3u) {
-        float2 r7;
-        st.dr = p8_dr<float2>(r2, st.dr, r7);
-        st.drmax = L::vmax(st.drmax, st.dr);
-        if (--left != 0u) {
-            float2 A, Zhn;
-            p8_elevation<float2>(pz, z2, L::bc(c.w), w2, A, Zhn);
-            st.zx = L::fma(A, L::bc(c.c8), st.px);
-            st.zy = L::fma(L::mul(A, L::bc(-2.0f)), L::bc(c.s8hn), st.py);
-            st.zz = L::fma(L::bc(-2.0f), Zhn, pz);
-            st.logp.x = polar_stretch_log(A.x, c.iw, r7.x);
-            st.logp.y = polar_stretch_log(A.y, c.iw, r7.y);
-            r2 = p8_pair_loop(st, bail2, left);
-        }
+    float2 r7;
+    dr = p8_dr<float2>(r2, dr, r7);
+    drmax = L::vmax(drmax, dr);
+    if (--left == 0u) {
+        if (!(done & 1u)) { d.x = de_fast_epilogue(r2.x, dr.x); if (fast_suspect_inside<kBand>(s, r2.x, drmax.x, 0)) suspect |= 1u; }
+        if (!(done & 2u)) { d.y = de_fast_epilogue(r2.y, dr.y); if (fast_suspect_inside<kBand>(s, r2.y, drmax.y, 0)) suspect |= 2u; }
+        return d;
     }
-    return p8_pair_finish<kBand>(s, st, r2, suspect);
+    float2 A, Zhn;
+    p8_elevation<float2>(pz, z2, L::bc(c.w), w2, A, Zhn);
+    const float2 zx = L::fma(A, L::bc(c.c8), px);
+    const float2 zy = L::fma(L::mul(A, L::bc(-2.0f)), L::bc(c.s8hn), py);
+    const float2 zz = L::fma(L::bc(-2.0f), Zhn, pz);
+    logp.x = polar_stretch_log(A.x, c.iw, r7.x);
+    logp.y = polar_stretch_log(A.y, c.iw, r7.y);
+    p8_pair_loop<kBand>(s, px, py, pz, zx, zy, zz, dr, drmax, logp, left, d, done, suspect);
+    return d;
 }
-#undef CTC_PAIR_ESCAPE
+#undef CTC_PAIR_ESCAPE_IMM
 
 // FAST generic-power DE of one sample (config 4's P = 2, 4, 16, ...): trig-free complex binary powers
 //   (z + i w)^P = r^P (cos P.theta + i sin P.theta),   ((x + i y)/w)^P = cos P.phi + i sin P.phi

@@ -125,8 +125,13 @@ struct SuspectList {
     uint32_t cap;
 };
 
+// fast / power 8: 64 registers, 4 CTAs per SM (A/B on the benched volume: 3 CTAs +8 %, 5 CTAs +1.5 %)
+#ifndef CTC_K1_MINBLOCKS
+#define CTC_K1_MINBLOCKS 4
+#endif
+
 template <bool kFast, int kVariant>
-__global__ void __launch_bounds__(kThreads, kFast && kVariant == kVarP8 ? 3 : 1)
+__global__ void __launch_bounds__(kThreads, kFast && kVariant == kVarP8 ? CTC_K1_MINBLOCKS : 1)
 sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r, float dvz8,
                     float* __restrict__ grids, size_t grid_stride,
                     uint32_t* __restrict__ sign_bits, uint32_t sign_stride /* words per span, 0 = no plane */,
@@ -563,43 +568,72 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
         const float p0y = M::add(g.s[1], M::mul((float)y, g.step[1]));
         const float p0z = M::add(g.s[2], M::mul((float)z, g.step[2]));
 
-        // corner coordinates p0 + corner_offsets[i] (buffer.rs:102-111, 242): the offset is 0.0 or step per axis
-        const float cx0 = M::add(p0x, 0.0f), cx1 = M::add(p0x, g.step[0]);
-        const float cy0 = M::add(p0y, 0.0f), cy1 = M::add(p0y, g.step[1]);
-        const float cz0 = M::add(p0z, 0.0f), cz1 = M::add(p0z, g.step[2]);
         // 12 edges (buffer.rs:155-176): from/to corner ids packed 4 bits each
         // x edges (0,4)(1,5)(2,6)(3,7); y edges (0,2)(1,3)(4,6)(5,7); z edges (0,1)(2,3)(4,5)(6,7)
         const unsigned long long kFrom = 0x642054103210ull, kTo = 0x753176327654ull;
-        int count = 0;
-        float sx_ = 0.0f, sy_ = 0.0f, sz_ = 0.0f;
+        float qx, qy, qz;
         bool bad = false;
+        if (kFast) {
+            // FAST: the centroid of the edge crossings in cell-local coordinates, branch-free.  The
+            // reference's (mirrored) weight (d_from + D) / D, D = d_to - d_from, is d_to / (d_to - d_from)
+            // whichever way the edge is oriented, and a crossing on an x edge sits at local
+            // (w, y_from, z_from): one reciprocal and a handful of selects per edge instead of twelve
+            // divergent regions with an IEEE division each (11 of 32 lanes active in round 1's profile).
+            float lx = 0.0f, ly = 0.0f, lz = 0.0f, cnt = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 12; ++e) {
-            const int from = (int)((kFrom >> (4 * e)) & 15ull), to = (int)((kTo >> (4 * e)) & 15ull);
-            const float df = dist[from], dt = dist[to];
-            if ((__float_as_uint(df) >> 31) == (__float_as_uint(dt) >> 31)) continue;   // :194-196
-            float d_from, d_to;
-            if (df < 0.0f) { d_from = df; d_to = dt; } else { d_from = -df; d_to = -dt; }   // :209-213
-            float w;
-            if (d_to == d_from) w = 0.5f;                                                  // :217-218
-            else { const float dl = M::sub(d_to, d_from); w = M::div(M::add(d_from, dl), dl); }   // :238-239
-            if (!(w >= 0.0f && w <= 1.0f)) bad = true;                                     // math.rs:19
-            const float om = M::sub(1.0f, w);
-            // lerp(p0 + off[from], p0 + off[to], w) = a*(1-w) + b*w   (math.rs:45-48)
-            const float ax = (from & 4) ? cx1 : cx0, bx = (to & 4) ? cx1 : cx0;
-            const float ay = (from & 2) ? cy1 : cy0, by = (to & 2) ? cy1 : cy0;
-            const float az = (from & 1) ? cz1 : cz0, bz = (to & 1) ? cz1 : cz0;
-            sx_ = M::add(sx_, M::add(M::mul(ax, om), M::mul(bx, w)));
-            sy_ = M::add(sy_, M::add(M::mul(ay, om), M::mul(by, w)));
-            sz_ = M::add(sz_, M::add(M::mul(az, om), M::mul(bz, w)));
-            ++count;
+            for (int e = 0; e < 12; ++e) {
+                const int from = (int)((kFrom >> (4 * e)) & 15ull), to = (int)((kTo >> (4 * e)) & 15ull);
+                const float df = dist[from], dt = dist[to];
+                const bool cross = ((__float_as_uint(df) ^ __float_as_uint(dt)) >> 31) != 0u;   // :194-196
+                const float den = dt - df;
+                const float w = den == 0.0f ? 0.5f : dt * fast_rcp(den);                         // :217-239
+                bad |= cross && !(w >= 0.0f && w <= 1.0f);                                       // math.rs:19
+                const float c = cross ? 1.0f : 0.0f, cw = cross ? w : 0.0f;
+                const int axis = (from ^ to);          // 4: x edge, 2: y edge, 1: z edge
+                lx += axis == 4 ? cw : ((from & 4) ? c : 0.0f);
+                ly += axis == 2 ? cw : ((from & 2) ? c : 0.0f);
+                lz += axis == 1 ? cw : ((from & 1) ? c : 0.0f);
+                cnt += c;
+            }
+            const float inv = fast_rcp(cnt);
+            qx = fmaf(lx * inv, g.step[0], p0x);
+            qy = fmaf(ly * inv, g.step[1], p0y);
+            qz = fmaf(lz * inv, g.step[2], p0z);
+        } else {
+            // corner coordinates p0 + corner_offsets[i] (buffer.rs:102-111, 242): the offset is 0.0 or step per axis
+            const float cx0 = M::add(p0x, 0.0f), cx1 = M::add(p0x, g.step[0]);
+            const float cy0 = M::add(p0y, 0.0f), cy1 = M::add(p0y, g.step[1]);
+            const float cz0 = M::add(p0z, 0.0f), cz1 = M::add(p0z, g.step[2]);
+            int count = 0;
+            float sx_ = 0.0f, sy_ = 0.0f, sz_ = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const int from = (int)((kFrom >> (4 * e)) & 15ull), to = (int)((kTo >> (4 * e)) & 15ull);
+                const float df = dist[from], dt = dist[to];
+                if ((__float_as_uint(df) >> 31) == (__float_as_uint(dt) >> 31)) continue;   // :194-196
+                float d_from, d_to;
+                if (df < 0.0f) { d_from = df; d_to = dt; } else { d_from = -df; d_to = -dt; }   // :209-213
+                float w;
+                if (d_to == d_from) w = 0.5f;                                                  // :217-218
+                else { const float dl = M::sub(d_to, d_from); w = M::div(M::add(d_from, dl), dl); }   // :238-239
+                if (!(w >= 0.0f && w <= 1.0f)) bad = true;                                     // math.rs:19
+                const float om = M::sub(1.0f, w);
+                // lerp(p0 + off[from], p0 + off[to], w) = a*(1-w) + b*w   (math.rs:45-48)
+                const float ax = (from & 4) ? cx1 : cx0, bx = (to & 4) ? cx1 : cx0;
+                const float ay = (from & 2) ? cy1 : cy0, by = (to & 2) ? cy1 : cy0;
+                const float az = (from & 1) ? cz1 : cz0, bz = (to & 1) ? cz1 : cz0;
+                sx_ = M::add(sx_, M::add(M::mul(ax, om), M::mul(bx, w)));
+                sy_ = M::add(sy_, M::add(M::mul(ay, om), M::mul(by, w)));
+                sz_ = M::add(sz_, M::add(M::mul(az, om), M::mul(bz, w)));
+                ++count;
+            }
+            // centroid (buffer.rs:247-250): origin + sum / count
+            const float fc = (float)count;
+            qx = M::add(0.0f, M::div(sx_, fc));
+            qy = M::add(0.0f, M::div(sy_, fc));
+            qz = M::add(0.0f, M::div(sz_, fc));
         }
         if (bad) atomicMin(&st->panic_span, span0 + span);
-        // centroid (buffer.rs:247-250): origin + sum / count
-        const float fc = (float)count;
-        const float qx = M::add(0.0f, M::div(sx_, fc));
-        const float qy = M::add(0.0f, M::div(sy_, fc));
-        const float qz = M::add(0.0f, M::div(sz_, fc));
 
         // dist_p and the un-normalised central differences (buffer.rs:254-265).
         // unit_x() * d = (1*d, 0*d, 0*d): the zero products keep their sign.  The reference multiplies
@@ -634,8 +668,11 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
         }
         const float nx = M::sub(de[1], de[2]), ny = M::sub(de[3], de[4]), nz = M::sub(de[5], de[6]);
         // cgmath normalize: v * (1 / sqrt((x*x + y*y) + z*z))
-        const float mag = M::sqrt(M::add(M::add(M::mul(nx, nx), M::mul(ny, ny)), M::mul(nz, nz)));
-        const float inv = M::div(1.0f, mag);
+        float inv;
+        if (kFast) inv = fast_rsqrt(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+        // (a squared length in the flush-to-zero range makes the approximation inf: take the IEEE route then)
+        if (!kFast || !(inv <= 1e18f))
+            inv = M::div(1.0f, M::sqrt(M::add(M::add(M::mul(nx, nx), M::mul(ny, ny)), M::mul(nz, nz))));
         float* o = out_v + slot * 7ull;
         o[0] = qx; o[1] = qy; o[2] = qz;
         o[3] = M::mul(nx, inv); o[4] = M::mul(ny, inv); o[5] = M::mul(nz, inv);

@@ -34,13 +34,13 @@ def test_hot_kernels_are_spill_free_and_within_register_budget():
         hits = [v for k, v in table.items() if all(n in k for n in needles)]
         assert len(hits) == 1, (needles, len(hits))
         return hits[0]
-    # K1 fast / power 8 (two samples per thread, packed FP32): 64 registers -> 4 CTAs of 256 threads per SM.
+    # K1 fast / power 8 (two samples per thread, packed FP32): launch bounds (256, 3) -> at most 85 registers.
     # The only stack use is the call frame of the out-of-line exact re-evaluation (suspects, rare).
     reg, stack, _, local = find("sample_grids_kernelILb1ELi0")
-    assert reg <= 64 and stack <= 64 and local == 0
-    # E3 fast / power 8: launch bounds (256, 5)
+    assert reg <= 85 and stack <= 64 and local == 0
+    # E3 fast / power 8: launch bounds (256, 4)
     reg, stack, _, local = find("vertex_kernelILb1ELi0")
-    assert reg <= 51 and stack <= 128 and local == 0
+    assert reg <= 64 and stack <= 128 and local == 0
     for name in ("classify_kernel", "apply_prefix_kernel", "quad_kernelILb0", "quad_kernelILb1", "expand_quads_kernel"):
         reg, stack, _, local = find(name)
         assert reg <= 64 and stack == 0 and local == 0, name
