@@ -69,6 +69,8 @@ EXPORTS = (
     "ctc_ray_march", "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
     "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
     "ctc_ctx_set_fast_band", "ctc_mesh_fixups", "ctc_fast_sign_probe", "ctc_sample_signs",
+    "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
+    "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
 )
 
 _lib = None
@@ -155,6 +157,24 @@ def lib() -> C.CDLL:
     L.ctc_sample_signs.argtypes = [vp, shp, spn, sz, u32, vp]
     L.ctc_fast_sign_probe.restype = C.c_int
     L.ctc_fast_sign_probe.argtypes = [vp, shp, spn, sz, u32, u64p, sz]
+    L.ctc_last_error_copy.restype = C.c_size_t
+    L.ctc_last_error_copy.argtypes = [vp, C.c_char_p, sz]
+    L.ctc_multi_create.restype = C.c_int
+    L.ctc_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.ctc_multi_destroy.restype = None
+    L.ctc_multi_destroy.argtypes = [vp]
+    L.ctc_multi_ngpus.restype = C.c_int
+    L.ctc_multi_ngpus.argtypes = [vp]
+    L.ctc_multi_ctx.restype = vp
+    L.ctc_multi_ctx.argtypes = [vp, C.c_int]
+    L.ctc_multi_last_error.restype = C.c_size_t
+    L.ctc_multi_last_error.argtypes = [vp, C.c_char_p, sz]
+    for name in ("ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, shp, spn, sz, u32, vp, sz, vp, sz, vp, vp, u64p, C.POINTER(CtcTimings)]
+    L.ctc_multi_shard_plan.restype = C.c_int
+    L.ctc_multi_shard_plan.argtypes = [sz, C.c_int, sz, sz, u64p, u64p, vp]
     L.ctc_fp32_peak_probe.restype = C.c_int
     L.ctc_fp32_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _lib = L
@@ -178,10 +198,12 @@ class Context:
 
     def check(self, rc: int):
         if rc != CTC_OK:
-            raise CantucciError(rc, lib().ctc_last_error(self._h).decode())
+            raise CantucciError(rc, self.last_error())
 
     def last_error(self) -> str:
-        return lib().ctc_last_error(self._h).decode()
+        buf = C.create_string_buffer(512)
+        lib().ctc_last_error_copy(self._h, buf, 512)      # copied out under the context's lock
+        return buf.value.decode(errors="replace")
 
     def set_stream(self, cuda_stream: int | None):
         self.check(lib().ctc_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
@@ -228,3 +250,55 @@ def default_context(device: int = 0) -> Context:
     if ctx is None:
         ctx = _default_ctx[device] = Context(device)
     return ctx
+
+
+def shard_plan(nspans: int, ngpus: int, vcap: int, icap: int):
+    """ctc_multi_shard_plan: (first_v [ngpus+1], first_i [ngpus+1], owner [nspans]) -- no GPU needed."""
+    first_v = np.zeros(ngpus + 1, dtype=np.uint64)
+    first_i = np.zeros(ngpus + 1, dtype=np.uint64)
+    owner = np.zeros(max(nspans, 1), dtype=np.uint32)
+    rc = lib().ctc_multi_shard_plan(nspans, ngpus, vcap, icap, first_v.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                    first_i.ctypes.data_as(C.POINTER(C.c_uint64)), owner.ctypes.data)
+    if rc != CTC_OK:
+        raise CantucciError(rc, "ctc_multi_shard_plan: invalid argument")
+    return first_v, first_i, owner[:nspans]
+
+
+class MultiContext:
+    """Owns a ctc_multi: one context + worker thread per GPU of this box, all in THIS process."""
+
+    def __init__(self, devices=None, ngpus: int = 0):
+        self._h = C.c_void_p()
+        arr = None
+        if devices is not None:
+            ngpus = len(devices)
+            arr = (C.c_int * ngpus)(*devices)
+        rc = lib().ctc_multi_create(arr, ngpus, C.byref(self._h))
+        if rc != CTC_OK:
+            self._h = C.c_void_p()
+            raise CantucciError(rc, "ctc_multi_create failed (no CUDA device? there is no CPU fallback)")
+        self.ngpus = int(lib().ctc_multi_ngpus(self._h))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def last_error(self) -> str:
+        buf = C.create_string_buffer(512)
+        lib().ctc_multi_last_error(self._h, buf, 512)
+        return buf.value.decode(errors="replace")
+
+    def check(self, rc: int):
+        if rc != CTC_OK:
+            raise CantucciError(rc, self.last_error())
+
+    def close(self):
+        if self._h:
+            lib().ctc_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

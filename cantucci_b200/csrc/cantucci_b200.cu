@@ -7,10 +7,12 @@
 #include "../../include/cantucci_b200.h"
 #include "kernels.cuh"
 
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ctc;
@@ -100,7 +102,7 @@ struct ctc_ctx {
 namespace {
 
 int fail(ctc_ctx* c, int code, const char* what) {
-    if (c) c->err = what;
+    if (c) c->err = std::string(what);       // (copies first: `what` may point into c->err's old buffer)
     return code;
 }
 int fail_cuda(ctc_ctx* c, cudaError_t e, const char* where) {
@@ -129,7 +131,7 @@ int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
     d.kind = s->kind;
     if (s->kind == CTC_SHAPE_MANDELBULB) {
         if (s->max_iters < 1) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "assert!(max_iters >= 1) (mandelbulb.rs:20)");
-        if (s->power < 1 || s->power > 255) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "power must be in 1..=255 (const generic P: u8)");
+        if (s->power < 1 || s->power > 255) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "power must be in 1..=255 (const generic P: u8; P = 0 has no r^(P-1))");
         d.power = s->power;
         d.max_iters = s->max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s->max_iters;
         d.bailout = s->bailout;
@@ -575,14 +577,17 @@ int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ct
         timings->first_ms = ms[0]; timings->second_ms = ms[1]; timings->third_ms = ms[2];
         timings->vertices = st->total_v; timings->faces = st->total_q;
     }
-    if (st->panic_span != 0xFFFFFFFFu) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "lerp factor outside [0,1] in span %u: the reference panics at math.rs:19", st->panic_span);
-        return fail(ctx, CTC_ERR_LERP_ASSERT, buf);
-    }
+    // A truncated output is reported ahead of the lerp assert ("mesh still delivered" must not hide a
+    // mesh that is NOT all there); the assert's span stays readable in the message either way.
+    char lerp[160] = "";
+    if (st->panic_span != 0xFFFFFFFFu)
+        snprintf(lerp, sizeof lerp, "lerp factor outside [0,1] in span %u: the reference panics at math.rs:19", st->panic_span);
     if (st->wire_overflow)
         return fail(ctx, CTC_ERR_OVERFLOW, "a span has >= 65536 vertices: packed quad records cannot carry it, use the u32 index wire");
-    if (st->overflow) return fail(ctx, CTC_ERR_OVERFLOW, "output capacity too small; required totals reported");
+    if (st->overflow)
+        return fail(ctx, CTC_ERR_OVERFLOW, (std::string("output capacity too small; required totals reported") +
+                                            (lerp[0] ? std::string("; also: ") + lerp : std::string())).c_str());
+    if (lerp[0]) return fail(ctx, CTC_ERR_LERP_ASSERT, lerp);
     return CTC_OK;
 }
 
@@ -694,6 +699,17 @@ int ctc_ctx_synchronize(ctc_ctx* ctx) {
 }
 
 const char* ctc_last_error(const ctc_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+size_t ctc_last_error_copy(ctc_ctx* ctx, char* buf, size_t len) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (buf && len) {
+        const size_t n = ctx->err.size() < len - 1 ? ctx->err.size() : len - 1;
+        memcpy(buf, ctx->err.data(), n);
+        buf[n] = 0;
+    }
+    return ctx->err.size();
+}
 
 uint64_t ctc_kernel_launches(const ctc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -1096,3 +1112,5 @@ int ctc_fp32_peak_probe(ctc_ctx* ctx, double* tflops, int* num_sms) {
 }
 
 }  // extern "C"
+
+#include "multi.inc"

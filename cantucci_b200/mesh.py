@@ -137,3 +137,56 @@ def generate_for_boxes(spans, shape: Shape, resolution: int, ctx: _lib.Context |
     nv, ni = int(v_off[ns]), int(i_off[ns])
     timings = Timings(t.first_ms, t.second_ms, t.third_ms, int(t.vertices), int(t.faces))
     return MeshBatch(v[:nv], idx[:ni], v_off, i_off), timings
+
+
+@dataclass
+class MultiMeshBatch:
+    """The meshes of many spans as ctc_mesh_spans_multi delivers them: flat buffers that are DEVICE-major
+    (every GPU fills its own region) and per-span [begin, end) tables in the caller's span order."""
+    vertices: np.ndarray     # VERTEX_DTYPE (host destination) or None (device destination)
+    indices: np.ndarray
+    span_v: np.ndarray       # u64 [nspans, 2]
+    span_i: np.ndarray       # u64 [nspans, 2]
+
+    def __len__(self) -> int:
+        return self.span_v.shape[0]
+
+    def mesh(self, k: int) -> MeshBuffer:
+        return MeshBuffer(self.vertices[int(self.span_v[k, 0]):int(self.span_v[k, 1])],
+                          self.indices[int(self.span_i[k, 0]):int(self.span_i[k, 1])])
+
+
+def generate_for_boxes_multi(spans, shape: Shape, resolution: int, multi: "_lib.MultiContext",
+                             vcap: int | None = None, icap: int | None = None):
+    """generate_for_box for every span, sharded over the GPUs of `multi` (ONE process: the span scheduler
+    behind the C ABI, ctc_mesh_spans_multi) -> (MultiMeshBatch, Timings).  Host destination; capacity is
+    guessed and the call is retried with the `need` the library reports on CTC_ERR_OVERFLOW."""
+    arr = spans_array(spans)
+    _check_args(arr, resolution)
+    ns = arr.shape[0]
+    if vcap is None:
+        vcap = max(4096, ns * 8 * resolution * resolution)
+    if icap is None:
+        icap = 6 * max(4096, ns * 8 * resolution * resolution)
+    sh = shape._ctc_shape()
+    span_v = np.zeros((ns, 2), dtype=np.uint64)
+    span_i = np.zeros((ns, 2), dtype=np.uint64)
+    need = (C.c_uint64 * 2)()
+    t = _lib.CtcTimings()
+    for _attempt in range(2):
+        v = np.empty(vcap, dtype=VERTEX_DTYPE)
+        idx = np.empty(icap, dtype=np.uint32)
+        rc = _lib.lib().ctc_mesh_spans_multi(multi.handle, C.byref(sh), arr.ctypes.data, ns, resolution,
+                                             v.ctypes.data, vcap, idx.ctypes.data, icap,
+                                             span_v.ctypes.data, span_i.ctypes.data, need, C.byref(t))
+        if rc == _lib.CTC_ERR_OVERFLOW:
+            vcap, icap = int(need[0]), int(need[1])
+            continue
+        if rc in (_lib.CTC_ERR_LERP_ASSERT, _lib.CTC_ERR_INVALID_ARGUMENT):
+            raise AssertionError(multi.last_error())
+        multi.check(rc)
+        break
+    else:
+        raise _lib.CantucciError(_lib.CTC_ERR_OVERFLOW, "output still too small after retry")
+    timings = Timings(t.first_ms, t.second_ms, t.third_ms, int(t.vertices), int(t.faces))
+    return MultiMeshBatch(v, idx, span_v, span_i), timings

@@ -31,6 +31,16 @@ def shard_indices(nspans: int, world: int, rank: int, mode: str = "interleave") 
     return np.arange(rank, nspans, world, dtype=np.int64)
 
 
+def agree_on_status(dist, torch, device, world: int, rc: int) -> int:
+    """Every rank learns the worst status of the step BEFORE any rank raises: a data-dependent failure on one
+    rank (CTC_ERR_LERP_ASSERT, CTC_ERR_OVERFLOW) must not leave the others waiting in a barrier / all-gather."""
+    if world <= 1:
+        return rc
+    t = torch.tensor([int(rc)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t[0])
+
+
 @dataclass
 class GatheredMeshes:
     """Rank 0's view after the gather.  Vertices/indices are rank-major (rank 0's spans, then
@@ -64,14 +74,23 @@ class DeviceMesher:
             self.v_off.data_ptr(), self.i_off.data_ptr())
         self.ctx.check(rc)
 
-    def result(self, allow_lerp_assert: bool = False):
+    def result_status(self):
+        """(status, vertices, indices, timings) without raising."""
         nv, ni = C.c_uint64(0), C.c_uint64(0)
         t = _lib.CtcTimings()
         rc = _lib.lib().ctc_mesh_result(self.ctx.handle, C.byref(nv), C.byref(ni), C.byref(t))
+        return rc, int(nv.value), int(ni.value), t
+
+    def result(self, allow_lerp_assert: bool = False):
+        rc, nv, ni, t = self.result_status()
         if rc == _lib.CTC_ERR_LERP_ASSERT and allow_lerp_assert:
-            rc = _lib.CTC_OK
+            # "mesh still delivered" only holds if nothing was truncated
+            if nv > self.vcap or ni > self.icap:
+                rc = _lib.CTC_ERR_OVERFLOW
+            else:
+                rc = _lib.CTC_OK
         self.ctx.check(rc)
-        return int(nv.value), int(ni.value), t
+        return nv, ni, t
 
 
 class SpanScheduler:
@@ -85,8 +104,8 @@ class SpanScheduler:
         if rank == 0 and world > 1:
             self.total_v = torch.empty((int(total_vcap), 7), dtype=torch.float32, device=device)
             self.total_i = torch.empty((int(total_icap),), dtype=torch.int32, device=device)
-        self.counts = torch.zeros((2,), dtype=torch.int64, device=device)
-        self.all_counts = torch.zeros((world, 2), dtype=torch.int64, device=device)
+        self.counts = torch.zeros((3,), dtype=torch.int64, device=device)          # vertices, indices, status
+        self.all_counts = torch.zeros((world, 3), dtype=torch.int64, device=device)
 
     def run(self, shape_struct, spans: np.ndarray, resolution: int) -> GatheredMeshes | None:
         torch, dist, world, rank = self.torch, self.dist, self.world, self.rank
@@ -107,11 +126,16 @@ class SpanScheduler:
                      vcap=self.total_v.shape[0], icap=self.total_i.shape[0])
         else:
             m.launch(shape_struct, local, resolution)
-        nv, ni, _ = m.result()
-        # exchange counts (2 x i64 per rank)
-        self.counts[0], self.counts[1] = nv, ni
+        rc, nv, ni, _ = m.result_status() if hasattr(m, "result_status") else (0, *m.result()[:2], None)
+        # exchange counts and the status (3 x i64 per rank): every rank completes the collective, then
+        # every rank raises the same error
+        self.counts[0], self.counts[1], self.counts[2] = nv, ni, rc
         dist.all_gather_into_tensor(self.all_counts.view(-1), self.counts)
         counts = self.all_counts.cpu().numpy()
+        worst = int(counts[:, 2].max())
+        if worst != _lib.CTC_OK:
+            bad = int(np.argmax(counts[:, 2]))
+            raise _lib.CantucciError(worst, f"rank {bad} failed the step" + (": " + m.ctx.last_error() if bad == rank and hasattr(m, "ctx") else ""))
         # variable-size gather: one grouped batch of NCCL send/recv
         ops, tables = [], None
         if rank == 0:
@@ -259,9 +283,11 @@ class PeerGatherScheduler:
             finally:
                 if self.wire_quads:
                     L.ctc_ctx_set_index_wire(ctx.handle, 0)
-        ctx.check(rc)
-        if world > 1:
-            self.dist.barrier()          # every rank's puts have completed (each call synchronised its copy stream)
+        # the status all-reduce doubles as the step's barrier: every rank's puts have completed (each call
+        # synchronised its copy streams), and a failure anywhere is raised on every rank
+        worst = agree_on_status(self.dist, self.torch, self.device, world, rc)
+        if worst != _lib.CTC_OK:
+            raise _lib.CantucciError(worst, ctx.last_error() if rc == worst else "another rank failed the step")
         if rank != 0:
             return None
         tables = self._views[2].cpu().numpy()      # one small D2H: every rank's offset tables
@@ -272,6 +298,7 @@ class PeerGatherScheduler:
                 src = self.ptrs[3].value + int(self.base_i[r]) // 6 * 8
                 dst = self.ptrs[1].value + int(self.base_i[r]) * 4
                 ctx.check(L.ctc_expand_quads(ctx.handle, src, nq, dst))
+            ctx.synchronize()            # the gathered index buffer is complete when run() returns
         return LazyGather(self, tables)
 
 
@@ -345,7 +372,8 @@ class HostGatherScheduler:
         self.off_v = 0
         self.off_i = al(int(self.base_v[-1]) * 28)
         self.off_t = self.off_i + al(int(self.base_i[-1]) * 4)
-        self.total = self.off_t + al(2 * int(self.base_t[-1]) * 8)
+        self.off_s = self.off_t + al(2 * int(self.base_t[-1]) * 8)          # one status word per rank
+        self.total = self.off_s + al(world * 8)
         names = [name or f"/dev/shm/cantucci_b200_gather_{os.getpid()}"]
         if world > 1:
             dist.broadcast_object_list(names, src=0)
@@ -359,11 +387,12 @@ class HostGatherScheduler:
         self._mm = mmap.mmap(self._f.fileno(), self.total)
         self.buf = np.frombuffer(self._mm, dtype=np.uint8)
         self._base = self.buf.ctypes.data
+        self._status = self.buf[self.off_s: self.off_s + world * 8].view(np.int64)
         # page-lock this rank's three regions (page-aligned supersets)
         self._pinned = []
         for lo, hi in ((self.off_v + int(self.base_v[rank]) * 28, self.off_v + int(self.base_v[rank + 1]) * 28),
                        (self.off_i + int(self.base_i[rank]) * 4, self.off_i + int(self.base_i[rank + 1]) * 4),
-                       (self.off_t, self.total)):
+                       (self.off_t, self.off_s)):
             lo_p, hi_p = lo // page * page, al(hi)
             ptr = self._base + lo_p
             if _lib.lib().ctc_host_register(ctx.handle, C.c_void_p(ptr), hi_p - lo_p) == _lib.CTC_OK:
@@ -396,9 +425,15 @@ class HostGatherScheduler:
         ti = self._base + self.off_t + (nt + int(self.base_t[rank])) * 8
         rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
                               pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti, None)
-        ctx.check(rc)
+        worst = rc
         if self.world > 1:
+            # statuses travel through the shared segment itself (one i64 per rank after the tables), so the
+            # barrier completes on every rank before any of them raises
+            self._status[rank] = rc
             self.dist.barrier()
+            worst = int(self._status[: self.world].max())
+        if worst != _lib.CTC_OK:
+            raise _lib.CantucciError(worst, ctx.last_error() if rc == worst else "another rank failed the step")
         if rank != 0:
             return None
         tables = self.buf[self.off_t: self.off_t + 2 * nt * 8].view(np.int64)

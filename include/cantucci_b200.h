@@ -119,8 +119,11 @@ CTC_API int ctc_ctx_set_group_spans(ctc_ctx *ctx, uint32_t spans_per_group);
  * serial kernels (per-pass timings then do not overlap; used for profiling). */
 CTC_API int ctc_ctx_set_overlap(ctc_ctx *ctx, int enable);
 CTC_API int ctc_ctx_synchronize(ctc_ctx *ctx);
-/* Human-readable description of the last failure on this context. */
+/* Human-readable description of the last failure on this context.  The pointer stays valid until the
+ * next failing call on the context: with several threads on ONE context use ctc_last_error_copy, which
+ * copies the message out under the context's lock (returns its full length; buf may be NULL). */
 CTC_API const char *ctc_last_error(const ctc_ctx *ctx);
+CTC_API size_t ctc_last_error_copy(ctc_ctx *ctx, char *buf, size_t len);
 /* Kernels launched by this context since creation (all entry points). */
 CTC_API uint64_t ctc_kernel_launches(const ctc_ctx *ctx);
 
@@ -178,6 +181,45 @@ CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indi
  * out_hit: n u32 (1 = Some(pos), 0 = None). */
 CTC_API int ctc_ray_march(ctc_ctx *ctx, const ctc_shape *shape, const float *origin, const float *dir, size_t n,
                           uint32_t max_steps, float epsilon, float *out_pos, uint32_t *out_hit);
+
+/* ---- span scheduler over the GPUs of one box (replaces ThreadPool::new(num_cpus) +
+ * mpsc channel, src/mesh/mod.rs:60-62, 129-161, for a single-process host) ------------------------------
+ *
+ * A ctc_multi owns one context and one worker thread per device.  A call deals the spans round-robin
+ * (span s -> device s % ngpus; neighbouring spans cost alike, so the deal balances the devices), every
+ * device meshes its share, and each device's launch groups are copied into ITS region of the caller's
+ * buffers while it computes the following groups: over NVLink into device memory of devices[0]
+ * (..._multi_device: "gather to rank 0"), or over each device's own PCIe link into host memory
+ * (..._multi).  Regions have fixed capacities (ctc_multi_shard_plan: proportional to span counts), so
+ * no count exchange and no collective is needed.
+ *
+ * Result layout: the vertices of span s are v[span_v[2s] .. span_v[2s+1]) and its indices
+ * idx[span_i[2s] .. span_i[2s+1]) (span-local ids, reference order); span_v / span_i are HOST arrays of
+ * 2 * nspans entries.  Completion order is free in the reference (results are keyed by span.center(),
+ * src/mesh/mod.rs:110-120, 147), so the buffers are device-major, not span-major.
+ * need (may be NULL): need[0] / need[1] = a vcap / icap with which the call cannot overflow (valid
+ * after CTC_OK or CTC_ERR_OVERFLOW: re-allocate and retry).  timings: per-pass maxima over the devices
+ * (they run concurrently), vertex / face totals. */
+typedef struct ctc_multi ctc_multi;
+/* devices: ngpus CUDA device ordinals, or NULL for 0 .. ngpus-1; ngpus <= 0: every device of the box. */
+CTC_API int ctc_multi_create(const int *devices, int ngpus, ctc_multi **out);
+CTC_API void ctc_multi_destroy(ctc_multi *m);
+CTC_API int ctc_multi_ngpus(const ctc_multi *m);
+/* The context of device i (ctc_ctx_set_group_spans, ctc_ctx_set_fast_band, ... apply per device). */
+CTC_API ctc_ctx *ctc_multi_ctx(ctc_multi *m, int i);
+CTC_API size_t ctc_multi_last_error(ctc_multi *m, char *buf, size_t len);
+CTC_API int ctc_mesh_spans_multi(ctc_multi *m, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                                 uint32_t resolution, ctc_vertex *v, size_t vcap, uint32_t *idx, size_t icap,
+                                 uint64_t *span_v, uint64_t *span_i, uint64_t need[2], ctc_timings *timings);
+/* d_v / d_idx: device memory of devices[0]. */
+CTC_API int ctc_mesh_spans_multi_device(ctc_multi *m, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                                        uint32_t resolution, ctc_vertex *d_v, size_t vcap, uint32_t *d_idx, size_t icap,
+                                        uint64_t *span_v, uint64_t *span_i, uint64_t need[2], ctc_timings *timings);
+/* The sharding and region tables of a call, without touching a GPU (also what the entry points use):
+ * first_v / first_i [ngpus + 1] = first vertex / index of every device's region (64-element aligned),
+ * owner [nspans] (may be NULL) = device position of every span. */
+CTC_API int ctc_multi_shard_plan(size_t nspans, int ngpus, size_t vcap, size_t icap, uint64_t *first_v,
+                                 uint64_t *first_i, uint32_t *owner);
 
 /* ---- peer memory for the multi-GPU gather -------------------------------- */
 

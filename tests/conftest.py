@@ -13,6 +13,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _device_count() -> int:
+    try:
+        import cantucci_b200 as cb
+        return int(cb.lib().ctc_device_count())
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """On a machine without a CUDA device the gpu-marked tests are SKIPPED (not errors): a plain `pytest`
+    run then separates real regressions from "no device"."""
+    if _device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (the product path has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 # BENCH_POINTS (/root/reference/src/shape/mod.rs:110-133): the reference's only fixture
 # for this path -- inputs only, it stores no expected outputs.
 BENCH_POINTS = np.array([
@@ -54,6 +73,8 @@ def oracle():
 @pytest.fixture(scope="session")
 def ctx():
     import cantucci_b200 as cb
+    if _device_count() == 0:
+        pytest.skip("no CUDA device (the product path has no CPU fallback)")
     return cb.default_context(0)
 
 
