@@ -10,12 +10,14 @@ job is N such volumes (one per rank: weak scaling, per-GPU work fixed) and every
 rank's vertex/index buffers are gathered to rank 0 over NVLink.
 
   python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
-  python bench.py --impl reference ...                     the CPU oracle (port of the reference's
-                                                           CPU path), all host threads, bounded sample
+  python bench.py --impl reference ...                     the CPU oracle (port of the reference's CPU path),
+                                                           all host threads, one whole volume per step
 
 Prints ONE JSON line (see the task contract): metric = DE samples/s of the whole
-step (samples evaluated in pass 1 / step time), plus `e2e`, `roofline`,
-`cpu_baseline`, `clocks`, `gpu_launches`.
+step (samples evaluated in pass 1 / step time), plus `e2e`, `roofline`, `parity`,
+`cpu_baseline`, `clocks`, `gpu_launches`, `strong_scaling` (BASELINE config 5: the
+4096^3 volume as 262 144 spans, ONE volume sharded over the N ranks), `other_configs`
+(BASELINE configs 1-4) and `small_batches` (latency of 1 / 8 / 64-span calls).
 """
 from __future__ import annotations
 
@@ -33,6 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+FLOPS_PER_ITERATION, FLOPS_BAILED, FLOPS_FIXED = 75.0, 6.0, 10.0       # flops(sample) = 75 k + 6 [bailed] + 10
 METRIC = "mandelbulb_de_samples_per_s"
 UNIT = "samples/s"
 TILES = 16          # 16^3 spans
@@ -125,30 +128,6 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
                 "samples": len(sm), "power_w_max": max(power), "where": where}
-
-
-# ---------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle (CPU port of the reference's path)
-# ---------------------------------------------------------------------------
-def cpu_sample_spans(spans: np.ndarray, stride: int) -> np.ndarray:
-    """A bounded, representative sample of the workload: the tiles with (ix + 3 iy + 5 iz) % stride == 0,
-    i.e. 1/stride of the spans spread evenly through the volume (interior, surface and empty
-    spans in their true mix)."""
-    t = round(spans.shape[0] ** (1.0 / 3.0))
-    i = np.arange(spans.shape[0])
-    ix, iy, iz = i // (t * t), (i // t) % t, i % t
-    return np.ascontiguousarray(spans[(ix + 3 * iy + 5 * iz) % stride == 0])
-
-
-def run_cpu(spans: np.ndarray, threads: int | None = None):
-    from oracle import oracle as O
-    sh = O.mandelbulb(POWER, MAX_ITERS, BAILOUT)
-    threads = threads or O.hardware_threads()
-    meshes, secs = O.generate_for_boxes_mt(sh, spans, RES, threads)
-    nv = sum(len(m[0]) for m in meshes if m is not None)
-    nq = sum(len(m[1]) // 6 for m in meshes if m is not None)
-    samples = spans.shape[0] * (RES + 1) ** 3
-    return {"secs": secs, "samples": samples, "spans": spans.shape[0], "threads": threads, "vertices": nv, "quads": nq}
 
 
 # ---------------------------------------------------------------------------
@@ -266,27 +245,36 @@ def gpu_volume_host(ctx, shape, spans: np.ndarray, vcap: int | None = None, icap
     return batch.vertices, batch.indices, batch.v_off, batch.i_off, planes
 
 
+def bench_config(world: int) -> dict:
+    """The `config` both arms print (identical keys and values, so the driver can compare them)."""
+    return {"workload": WORKLOAD, "volumes": world, "spans": world * TILES ** 3, "spans_per_volume": TILES ** 3,
+            "samples_per_step": world * TILES ** 3 * (RES + 1) ** 3, "resolution": RES, "power": POWER,
+            "max_iters": MAX_ITERS, "bailout": BAILOUT,
+            "scaling": "weak: one 1024^3 volume per GPU, every rank's meshes gathered to rank 0",
+            "l2": "per-step working set (4.5 GB of sample grids streamed in 512 MiB launch groups + 0.7 GB of mesh "
+                  "per volume) exceeds the 126 MB L2; no explicit flush"}
+
+
 def reference_main(args):
-    rank = env_int("RANK", 0)
+    """The reference arm: the CPU port of the reference's path on all host threads (one span per task, like
+    ThreadPool::new(num_cpus), mesh/mod.rs:61-62,141), ONE whole volume (all 4096 spans) per step."""
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     if rank != 0:
         return 0
     spans = workload_spans()
-    sample = cpu_sample_spans(spans, 4)           # 1024 of the 4096 spans per step
-    times = []
-    res = None
+    times, res = [], None
     for s in range(args.warmup + args.steps):
-        res = run_cpu(sample)
+        res = oracle_volume(spans, signs=False)
         if s >= args.warmup:
             times.append(res["secs"])
     t = float(np.mean(times))
     value = res["samples"] / t
-    desc = f"{res['spans']} of {spans.shape[0]} spans per step (tiles with (ix+3iy+5iz)%4==0, spread evenly through the volume)"
+    desc = (f"all {res['spans']} spans of one 1024^3 volume per step, {res['threads']} host threads"
+            + ("" if world == 1 else f" (the job of this config is {world} such volumes; the CPU rate does not depend on it)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "spans": int(spans.shape[0]), "resolution": RES, "power": POWER,
-                   "max_iters": MAX_ITERS, "bailout": BAILOUT, "cpu_sample": desc},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(world),
         "span_meshes_per_s": res["spans"] / t,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -302,7 +290,7 @@ def ours_main(args):
     import torch
     import torch.distributed as dist
     import cantucci_b200 as cb
-    from cantucci_b200 import _lib
+    from cantucci_b200 import _lib, refine
     from cantucci_b200.scheduler import (DeviceMesher, HostGatherScheduler, PeerGatherScheduler, SpanScheduler,
                                          shard_indices)
 
@@ -313,8 +301,10 @@ def ours_main(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
     ctx = cb.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=device)          # a real (non-default) stream: the context adopts it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     if args.group_spans:
         ctx.set_group_spans(args.group_spans)
@@ -322,63 +312,80 @@ def ours_main(args):
     fast = not args.exact
     shape = cb.Mandelbulb.classic(MAX_ITERS, BAILOUT, fast=fast)
     sh = shape._ctc_shape()
-    volume = workload_spans(args.tiles)
-    strong = args.scaling == "strong"
-    if strong:
-        # ONE volume, spans dealt round-robin over the ranks (total work fixed)
-        spans, shard_mode = volume, "interleave"
-    else:
-        # weak scaling (default): the job is `world` volumes, one per rank (block sharding keeps per-rank work identical)
-        spans, shard_mode = np.ascontiguousarray(np.tile(volume, (world, 1))), "block"
-    nspans = spans.shape[0]
-    mine = shard_indices(nspans, world, rank, shard_mode)
     n3 = (RES + 1) ** 3
-    total_samples = nspans * n3
-
-    # capacities from one sizing run of this rank's shard (outside the timed region)
-    probe = DeviceMesher(ctx, torch, device, 1, 6, len(mine))
-    probe.launch(sh, np.ascontiguousarray(spans[mine]), RES)
-    ctx.check(0)
-    nv_req, ni_req = C.c_uint64(0), C.c_uint64(0)
-    _lib.lib().ctc_mesh_result(ctx.handle, C.byref(nv_req), C.byref(ni_req), None)
-    nv_loc, ni_loc = int(nv_req.value), int(ni_req.value)
-    # the packed quad wire needs every span to stay below 65536 vertices: check it on the sizing run
-    max_span_v = int(probe.v_off[: len(mine) + 1].diff().max()) if len(mine) else 0
-    del probe
-    tot = torch.tensor([nv_loc, ni_loc], dtype=torch.int64, device=device)
-    mx = torch.tensor([max_span_v], dtype=torch.int64, device=device)
-    if world > 1:
-        dist.all_reduce(tot)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    packed_ok = int(mx[0]) < 65536
-    nv_tot, ni_tot = int(tot[0]), int(tot[1])
     pad = lambda n: int(n * 1.02) + 1024
-    # packed quad records pay off once rank 0's NVLink ingest is the bound (measured: 8 GPUs); below that
-    # the widening pass on rank 0 costs more than the smaller gather saves (4 GPUs: 6.97 vs 6.82 ms)
-    use_packed = (args.gather == "peer" and not args.wire_u32 and packed_ok and (world > 4 or args.wire_packed))
-    if world > 1 and args.gather in ("peer", "direct"):
-        caps = torch.zeros((world, 2), dtype=torch.int64, device=device)
-        caps[rank, 0], caps[rank, 1] = pad(nv_loc), pad(ni_loc)
-        dist.all_reduce(caps)
-        caps = caps.cpu().numpy()
-        sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
-                                    mode=shard_mode, direct=(args.gather == "direct"),
-                                    wire_quads=use_packed)
-    else:
-        mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
-        sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
-
-    local_spans = np.ascontiguousarray(spans[mine])
-
-    def step():
-        if isinstance(sched, PeerGatherScheduler):
-            return sched.run(sh, spans, RES, local=local_spans)
-        return sched.run(sh, spans, RES)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def sizing(local_spans):
+        """Capacities of a shard from one run with a 1-vertex buffer (the library reports what it needs)."""
+        probe = DeviceMesher(ctx, torch, device, 1, 6, len(local_spans))
+        probe.launch(sh, local_spans, RES)
+        rc, nv, ni, _ = probe.result_status()
+        if rc not in (_lib.CTC_OK, _lib.CTC_ERR_OVERFLOW):
+            ctx.check(rc)
+        max_span_v = int(probe.v_off[: len(local_spans) + 1].diff().max()) if len(local_spans) else 0
+        return nv, ni, max_span_v
+
+    def make_scheduler(spans, shard_mode, gather, wire_packed_from):
+        """(scheduler, local spans, totals) for one job: `spans` sharded over the ranks, gathered to rank 0."""
+        nspans = spans.shape[0]
+        mine = shard_indices(nspans, world, rank, shard_mode)
+        local = np.ascontiguousarray(spans[mine])
+        nv_loc, ni_loc, max_span_v = sizing(local)
+        tot = torch.tensor([nv_loc, ni_loc], dtype=torch.int64, device=device)
+        mx = torch.tensor([max_span_v], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(tot)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        nv_tot, ni_tot = int(tot[0]), int(tot[1])
+        # packed quad records pay off once rank 0's NVLink ingest is the bound (measured: 8 GPUs); they need every
+        # span below 65536 vertices (checked on the sizing run)
+        use_packed = gather == "peer" and not args.wire_u32 and int(mx[0]) < 65536 and (world >= wire_packed_from or args.wire_packed)
+        if world > 1 and gather in ("peer", "direct"):
+            caps = torch.zeros((world, 2), dtype=torch.int64, device=device)
+            caps[rank, 0], caps[rank, 1] = pad(nv_loc), pad(ni_loc)
+            dist.all_reduce(caps)
+            caps = caps.cpu().numpy()
+            sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
+                                        mode=shard_mode, direct=(gather == "direct"), wire_quads=use_packed)
+        else:
+            mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
+            sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
+        info = {"nspans": nspans, "mine": len(mine), "nv_loc": nv_loc, "ni_loc": ni_loc, "nv_tot": nv_tot, "ni_tot": ni_tot,
+                "packed": bool(use_packed),
+                "gathered_bytes": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (8 / 6 if use_packed else 4))}
+        return sched, local, info
+
+    def run_step(sched, spans, local):
+        if isinstance(sched, PeerGatherScheduler):
+            return sched.run(sh, spans, RES, local=local)
+        return sched.run(sh, spans, RES)
+
+    def timed_steps(fn, steps):
+        """`steps` calls of fn between CUDA events on the launching stream, barrier + sync on both sides;
+        returns ms per step, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / steps
+
+    # ======================================================================== headline: weak scaling ====
+    volume = workload_spans(args.tiles)
+    spans = volume if world == 1 else np.ascontiguousarray(np.tile(volume, (world, 1)))
+    sched, local_spans, info = make_scheduler(spans, "block", args.gather, wire_packed_from=5)
+    nspans, total_samples = info["nspans"], info["nspans"] * n3
+    step = lambda: run_step(sched, spans, local_spans)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -388,189 +395,226 @@ def ours_main(args):
     barrier()
     launches1 = ctx.kernel_launches()
     sampler.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pass_ms = np.zeros(3)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
+    ms_per_step = timed_steps(step, args.steps)
     sampler.mark_end()
-    ms = e0.elapsed_time(e1)
     launches2 = ctx.kernel_launches()
-    # pass timings of the last step (CUDA events on the launching stream, inside the timed region)
-    t = _lib.CtcTimings()
-    _lib.lib().ctc_mesh_result(ctx.handle, None, None, C.byref(t))
-    pass_ms[:] = (t.first_ms, t.second_ms, t.third_ms)
-    # the same step once more with strictly serial kernels: per-kernel times without SM sharing
-    serial_ms = np.zeros(3)
-    ctx.set_overlap(False)
-    step(); step()
-    _lib.lib().ctc_mesh_result(ctx.handle, None, None, C.byref(t))
-    serial_ms[:] = (t.first_ms, t.second_ms, t.third_ms)
-    ctx.set_overlap(True)
-    tms = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tms[0]) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    t = _lib.CtcTimings()
+    L.ctc_mesh_result(ctx.handle, None, None, C.byref(t))
+    pass_ms_region = [t.first_ms, t.second_ms, t.third_ms]     # last step of the timed region (kernels overlapped)
+    suspects, sign_fixups = ctx.mesh_fixups()
+    # the same step with strictly serial kernels and an event pair around every kernel: per-kernel device times
+    ctx.set_overlap(False); ctx.set_kernel_timing(True)
+    step(); step()
+    L.ctc_mesh_result(ctx.handle, None, None, C.byref(t))
+    pass_ms_serial = [t.first_ms, t.second_ms, t.third_ms]
+    kernel_ms = ctx.kernel_times()
+    ctx.set_overlap(True); ctx.set_kernel_timing(False)
     value = total_samples / (ms_per_step * 1e-3)
 
-    # ---- e2e at N > 1: HOST buffers.  Every rank meshes its volume through the host-pointer C ABI call
-    # (ctc_mesh_spans) into ITS region of one shared, page-locked host segment, i.e. the device->host
-    # copies of the N ranks run in parallel over N PCIe links; rank 0 reads all offset tables there.
-    e2e_multi = None
-    shm_ok = True
-    if world > 1:
-        # the shared segment lives in /dev/shm: make sure it fits before every rank commits to it
-        import shutil
-        need = int((nv_tot * 28 + ni_tot * 4) * 1.1) + (64 << 20)
-        flag = torch.tensor([1 if (rank != 0 or shutil.disk_usage("/dev/shm").free > need) else 0],
-                            dtype=torch.int64, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        shm_ok = bool(int(flag[0]))
-        if not shm_ok:
-            e2e_multi = {"value": None, "unit": UNIT, "note": f"/dev/shm cannot hold the {need >> 20} MiB shared host segment"}
-    if world > 1 and shm_ok:
-        capsh = torch.zeros((world, 2), dtype=torch.int64, device=device)
-        capsh[rank, 0], capsh[rank, 1] = pad(nv_loc), pad(ni_loc)
-        dist.all_reduce(capsh)
-        capsh = capsh.cpu().numpy()
-        hs = HostGatherScheduler(dist, ctx, rank, world, nspans, capsh[:, 0].tolist(), capsh[:, 1].tolist(), mode=shard_mode)
-        d2h = [0]
+    # ======================================================================== BASELINE config 5: strong scaling ====
+    strong = None
+    if not args.no_strong and args.tiles == TILES:
+        vol5 = workload_spans(64)                          # the 4096^3 volume as 64^3 spans of R = 64: 262 144 spans
+        sched5, local5, info5 = make_scheduler(vol5, "interleave", args.gather, wire_packed_from=5)
+        step5 = lambda: run_step(sched5, vol5, local5)
+        step5()
+        ms5 = timed_steps(step5, args.strong_steps)
+        L.ctc_mesh_result(ctx.handle, None, None, C.byref(t))
+        mine_ms = torch.tensor([t.first_ms + t.second_ms + t.third_ms], dtype=torch.float64, device=device)
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(all_ms, mine_ms)
+        else:
+            all_ms = [mine_ms]
+        strong = {"workload": "mandelbulb_p8_i6_b2.5_bbox_4096cube_as_64x64x64_spans_R64 (BASELINE config 5)",
+                  "scaling": "strong", "spans": int(info5["nspans"]), "spans_per_gpu": int(info5["mine"]),
+                  "samples": int(info5["nspans"]) * n3, "ms_per_step": ms5, "steps": args.strong_steps,
+                  "value": info5["nspans"] * n3 / (ms5 * 1e-3), "unit": UNIT,
+                  "span_meshes_per_s": info5["nspans"] / (ms5 * 1e-3),
+                  "vertices": info5["nv_tot"], "indices": info5["ni_tot"],
+                  "sharding": "one volume, spans dealt round-robin over the ranks; meshes gathered to rank 0"
+                              + ("" if world == 1 else " by one-sided copy-engine puts over NVLink, pipelined behind compute"),
+                  "index_wire": "packed 8-byte quads, widened on rank 0" if info5["packed"] else "six u32 per quad",
+                  "rank0_ingest_bytes_per_step": info5["gathered_bytes"],
+                  "rank0_ingest_gb_s": info5["gathered_bytes"] / (ms5 * 1e-3) / 1e9,
+                  "kernel_ms_per_rank_last_step": [float(x[0]) for x in all_ms],
+                  "note": "speed-up over N = 1 is this value divided by the N = 1 run's strong_scaling.value"}
+        if hasattr(sched5, "close"):
+            sched5.close()
+        del sched5, local5
+        torch.cuda.empty_cache()
 
-        def e2e_step_multi():
-            g = hs.run(sh, spans, RES, local=local_spans)
-            if rank == 0:
-                d2h[0] = g.n_vertices * 28 + g.n_indices * 4 + 2 * (nspans + world) * 8
-        for _ in range(2):
-            e2e_step_multi()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(n_e2e):
-            e2e_step_multi()
-        barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=device)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        hs.close()
-        e2e_multi = {"value": total_samples / float(dt[0]), "unit": UNIT, "ms_per_step": float(dt[0]) * 1e3,
-                     "h2d_bytes_per_step": int(nspans * 48), "d2h_bytes_per_step": int(d2h[0]),
-                     "api": "ctc_mesh_spans on every rank into one shared page-locked host segment "
-                            "(HostGatherScheduler: N device->host copies in parallel over N PCIe links)", "steps": n_e2e}
+    # ======================================================================== e2e at N > 1: HOST buffers ====
+    # Every rank meshes its volume through the host-pointer C ABI call (ctc_mesh_spans) into ITS region of one
+    # shared, page-locked host segment, i.e. the device->host copies of the N ranks run in parallel over N PCIe
+    # links; rank 0 reads all offset tables there.
+    e2e_multi = None
+    if world > 1:
+        import shutil
+        need = int((info["nv_tot"] * 28 + info["ni_tot"] * 4) * 1.1) + (64 << 20)
+        flag = torch.tensor([1 if (rank != 0 or shutil.disk_usage("/dev/shm").free > need) else 0], dtype=torch.int64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag[0]):
+            e2e_multi = {"value": None, "unit": UNIT, "note": f"/dev/shm cannot hold the {need >> 20} MiB shared host segment"}
+        else:
+            capsh = torch.zeros((world, 2), dtype=torch.int64, device=device)
+            capsh[rank, 0], capsh[rank, 1] = pad(info["nv_loc"]), pad(info["ni_loc"])
+            dist.all_reduce(capsh)
+            capsh = capsh.cpu().numpy()
+            hs = HostGatherScheduler(dist, ctx, rank, world, nspans, capsh[:, 0].tolist(), capsh[:, 1].tolist(), mode="block")
+            d2h = [0]
+
+            def e2e_step_multi():
+                g = hs.run(sh, spans, RES, local=local_spans)
+                if rank == 0:
+                    d2h[0] = g.n_vertices * 28 + g.n_indices * 4 + 2 * (nspans + world) * 8
+            for _ in range(2):
+                e2e_step_multi()
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = args.steps
+            for _ in range(n_e2e):
+                e2e_step_multi()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=device)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            hs.close()
+            e2e_multi = {"value": total_samples / float(dt[0]), "unit": UNIT, "ms_per_step": float(dt[0]) * 1e3,
+                         "h2d_bytes_per_step": int(nspans * 48), "d2h_bytes_per_step": int(d2h[0]),
+                         "api": "ctc_mesh_spans on every rank into one shared page-locked host segment "
+                                "(HostGatherScheduler: N device->host copies in parallel over N PCIe links)", "steps": n_e2e}
 
     line = None
     if rank == 0:
         peaks = read_peaks()
-        # ---- algorithmic flops of the dominant kernel (pass 1, sample_grids_kernel) -------------
+        hbm_gbs = peaks.get("hbm_gbs") or 6650.0
+        hbm_src = "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks.get("hbm_gbs") else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # ---- algorithmic flops: pass 1 (K1) from the iteration counts of this rank's sample lattices ----------
         stats = (C.c_uint64 * 3)()
-        sub = local_spans
-        ctx.check(_lib.lib().ctc_iteration_stats(ctx.handle, C.byref(sh), sub.ctypes.data, sub.shape[0], RES, stats))
+        ctx.check(L.ctc_iteration_stats(ctx.handle, C.byref(sh), local_spans.ctypes.data, local_spans.shape[0], RES, stats))
         sum_k, n_bailed, n_s = int(stats[0]), int(stats[1]), int(stats[2])
-        flops_pass1 = 75.0 * sum_k + 6.0 * n_bailed + 10.0 * n_s
-        # pass 1's kernel time: from the serial replay when the timed region overlapped it with the
-        # previous group's extraction (both are reported)
-        k1_ms = float(serial_ms[0])
-        achieved = flops_pass1 / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+        flops_pass1 = FLOPS_PER_ITERATION * sum_k + FLOPS_BAILED * n_bailed + FLOPS_FIXED * n_s
+        # ---- ... and pass 2's seven DE evaluations per vertex (E3), on the points the kernel evaluates ---------
+        flops_e3 = None
+        if world == 1:
+            m = sched.mesher
+            nv = info["nv_loc"]
+            pos = m.v[:nv, :3]
+            across = np.float32(np.float32(np.float32(local_spans[0, 3] + (local_spans[0, 3] - local_spans[0, 0]) / np.float32(RES))
+                                           - np.float32(local_spans[0, 0] - (local_spans[0, 3] - local_spans[0, 0]) / np.float32(RES))))
+            delta = float(np.float32(np.float32(0.7) * across) / np.float32(RES))        # uniform tiles: one delta
+            offs = torch.tensor([[0, 0, 0], [delta, 0, 0], [-delta, 0, 0], [0, delta, 0], [0, -delta, 0], [0, 0, delta], [0, 0, -delta]],
+                                dtype=torch.float32, device=device)
+            pts = (pos[:, None, :] + offs[None, :, :]).reshape(-1, 3).contiguous()
+            torch.cuda.synchronize()
+            ctx.check(L.ctc_iteration_stats_points(ctx.handle, C.byref(sh), pts.data_ptr(), pts.shape[0], stats))
+            flops_e3 = FLOPS_PER_ITERATION * int(stats[0]) + FLOPS_BAILED * int(stats[1]) + 4.0 * int(stats[2])
+            del pts
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         probe_tf, sms = C.c_double(0.0), C.c_int(0)
-        _lib.lib().ctc_fp32_peak_probe(ctx.handle, C.byref(probe_tf), C.byref(sms))
+        L.ctc_fp32_peak_probe(ctx.handle, C.byref(probe_tf), C.byref(sms))
         nominal = (sms.value or 148) * 128 * 2 * sm_max * 1e6 / 1e12
+        k1_ms = kernel_ms["sample_grids"] + kernel_ms["fixup_suspects"]       # pass 1 = K1 + its sign repair
+        achieved = flops_pass1 / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic_r2.json")))["dram_bytes_per_volume"]
         except Exception:
             pass
         roofline = {
-            "bound": "fp32", "kernel": "sample_grids_kernel (pass 1: DE over the span sample grids)",
+            "bound": "fp32", "kernel": "sample_grids_kernel + fixup_suspects_kernel (pass 1: DE over the span sample grids, "
+                                       "sign repair included), per 1024^3 volume, timed with serial kernels outside the "
+                                       "timed region (inside it K1 shares the SMs with the previous group's extraction: see "
+                                       "pass_ms_timed_region_overlapped)",
             "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal if nominal else None,
             "traffic": traffic,
-            "peak_source": f"no FP32 figure in MEASURED_PEAKS.json: SMs x 128 lanes x 2 x clocks.max.sm = {sms.value} x 128 x 2 x {sm_max:.0f} MHz",
+            "traffic_source": "profile constant: dram__bytes_read.sum + dram__bytes_write.sum of the 9 K1 launches of one volume, "
+                              "ncu --set full (profiles/k1_traffic_r2.json); not measured in this run",
+            "peak_source": f"no FP32 figure in MEASURED_PEAKS.json: nominal SMs x 128 lanes x 2 x clocks.max.sm = {sms.value} x 128 x 2 x {sm_max:.0f} MHz",
             "peak_measured_fma_tflops": probe_tf.value,
+            "peak_note": "the nominal peak needs FMAs with an immediate/constant operand; a stream of FFMA (or packed FFMA2) with three "
+                         "register operands sustains 42-49 TFLOP/s on this part (register-file read bandwidth, scripts/ubench_fp32x2.cu, "
+                         "profiles/ubench_fp32x2_r2.txt)",
             "frac_of_measured_fma": achieved / probe_tf.value if probe_tf.value else None,
-            "algorithmic_flops_per_launch_group": flops_pass1, "mean_iterations_per_sample": sum_k / max(n_s, 1),
-            "kernel_ms_per_step": k1_ms,
-            "passes_ms_timed_region_overlapped": {"first_de": pass_ms[0], "second_classify_vertices": pass_ms[1], "third_quads": pass_ms[2]},
-            "passes_ms_serial_replay": {"first_de": serial_ms[0], "second_classify_vertices": serial_ms[1], "third_quads": serial_ms[2]},
-            "hbm_gbs_measured": peaks.get("hbm_gbs"),
+            "algorithmic_flops_per_volume": flops_pass1, "mean_iterations_per_sample": sum_k / max(n_s, 1),
+            "kernel_ms_per_volume": k1_ms, "kernel_ms_serial_per_volume": kernel_ms,
+            "pass_ms_timed_region_overlapped": dict(zip(("first_de", "second_classify_vertices", "third_quads"), pass_ms_region)),
+            "pass_ms_serial": dict(zip(("first_de", "second_classify_vertices", "third_quads"), pass_ms_serial)),
+            "sign_repair": {"suspects_per_volume": suspects, "sign_fixups_per_volume": sign_fixups},
         }
-        # ---- e2e: host buffers through the public C ABI call (ctc_mesh_spans), copies included ---
-        e2e = e2e_multi
+        # ---- extraction: HBM roofline of the byte-moving kernels (E1 classify, E2b prefix, E4 quads) -------------
+        V, Q = info["nv_loc"], info["ni_loc"] // 6
+        ext_bytes = len(local_spans) * n3 / 8.0 + 28.0 * V + 24.0 * Q           # SURVEY 8d, fused form: sign bits + vertices + indices
+        ext_ms = kernel_ms["classify"] + kernel_ms["apply_prefix"] + kernel_ms["quads"]
+        roofline_extraction = {
+            "bound": "hbm", "kernels": "classify_kernel + apply_prefix_kernel + quad_kernel (E1 + E2b + E4), per volume, serial kernels",
+            "algorithmic_bytes": ext_bytes, "formula": "n^3/8 per span (sign bit-plane) + 28 V + 24 Q (SURVEY 8d, fused form)",
+            "ms": ext_ms, "achieved": ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
+            "frac": ext_bytes / (ext_ms * 1e-3) / 1e9 / hbm_gbs if ext_ms > 0 else None, "peak_source": hbm_src,
+            "scan_chunks_ms": kernel_ms["scan_chunks"],
+        }
+        whole = None
+        if flops_e3 is not None:
+            whole = {"algorithmic_flops": flops_pass1 + flops_e3, "pass1_flops": flops_pass1, "pass2_de_flops": flops_e3,
+                     "ms_per_step": ms_per_step, "tflops": (flops_pass1 + flops_e3) / (ms_per_step * 1e-3) / 1e12,
+                     "frac_of_nominal_fp32": (flops_pass1 + flops_e3) / (ms_per_step * 1e-3) / 1e12 / nominal,
+                     "pass1_only_frac_of_nominal_fp32": flops_pass1 / (ms_per_step * 1e-3) / 1e12 / nominal,
+                     "vertex_kernel_tflops": flops_e3 / (kernel_ms["vertex"] * 1e-3) / 1e12 if kernel_ms["vertex"] > 0 else None}
+        # ---- e2e (N = 1): host buffers through the public C ABI call (ctc_mesh_spans), copies included ---------
+        e2e, parity, cpu = e2e_multi, None, None
         if world == 1:
-            v_host = torch.empty((pad(nv_tot), 7), dtype=torch.float32).pin_memory()
-            i_host = torch.empty((pad(ni_tot),), dtype=torch.int32).pin_memory()
+            v_host = torch.empty((pad(info["nv_tot"]), 7), dtype=torch.float32).pin_memory()
+            i_host = torch.empty((pad(info["ni_tot"]),), dtype=torch.int32).pin_memory()
             v_off = np.zeros(nspans + 1, dtype=np.uint64); i_off = np.zeros(nspans + 1, dtype=np.uint64)
+
             def e2e_step():
-                rc = _lib.lib().ctc_mesh_spans(ctx.handle, C.byref(sh), spans.ctypes.data, nspans, RES,
-                                               v_host.data_ptr(), v_host.shape[0], i_host.data_ptr(), i_host.shape[0],
-                                               v_off.ctypes.data, i_off.ctypes.data, None)
-                ctx.check(rc)
-            for _ in range(max(1, min(args.warmup, 3))):
+                ctx.check(L.ctc_mesh_spans(ctx.handle, C.byref(sh), spans.ctypes.data, nspans, RES, v_host.data_ptr(), v_host.shape[0],
+                                           i_host.data_ptr(), i_host.shape[0], v_off.ctypes.data, i_off.ctypes.data, None))
+            for _ in range(3):
                 e2e_step()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            n_e2e = max(3, min(args.steps, 10))
-            for _ in range(n_e2e):
+            for _ in range(args.steps):
                 e2e_step()
             torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n_e2e
+            dt = (time.perf_counter() - t0) / args.steps
             nv, ni = int(v_off[nspans]), int(i_off[nspans])
-            e2e = {"value": total_samples / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-                   "h2d_bytes_per_step": int(nspans * 48),
+            e2e = {"value": total_samples / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(nspans * 48),
                    "d2h_bytes_per_step": int(nv * 28 + ni * 4 + 2 * (nspans + 1) * 8 + 48),
-                   "api": "ctc_mesh_spans (host pointers; pinned host buffers)", "steps": n_e2e}
-        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ---------------
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            sample = cpu_sample_spans(spans, 4)
-            r = run_cpu(sample)
-            cpu = {"value": r["samples"] / r["secs"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                   "sample": f"{r['spans']} of {nspans} spans (tiles with (ix+3iy+5iz)%stride==0), {r['secs']:.2f} s",
-                   "span_meshes_per_s": r["spans"] / r["secs"]}
-        # ---- the other BASELINE.json configs, briefly (N = 1 only; parity for them lives in tests/) ---------
-        other = None
-        if world == 1 and args.tiles == TILES:
-            other = {}
-
-            def timed(fn, reps):
-                fn(); torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                for _ in range(reps):
-                    fn()
-                b.record(stream); torch.cuda.synchronize()
-                return a.elapsed_time(b) / reps
-            # config 1: the 64 startup leaves (mesh/mod.rs:52-56), device-resident
-            startup = cb.spans_array([n.span for n in cb.startup_tree(shape.bounding_box()).leaves()])
-            m1 = DeviceMesher(ctx, torch, device, 700_000, 4_200_000, 64)
-            ms1 = timed(lambda: (m1.launch(sh, startup, RES), m1.result()), 20)
-            other["config1_startup_octree_64_spans_R64"] = {"ms": ms1, "samples_per_s": 64 * n3 / (ms1 * 1e-3),
-                                                            "span_meshes_per_s": 64 / (ms1 * 1e-3)}
-            # config 2: dense 512^3 DE sample grid, one bbox span (pass 1 only: meshing this span panics in the reference)
-            bbox = np.array([[-1.2, -1.2, -1.2, 1.2, 1.2, 1.2]], dtype=np.float32)
-            g512 = torch.empty((513 ** 3,), dtype=torch.float32, device=device)
-            ms2 = timed(lambda: ctx.check(_lib.lib().ctc_sample_grids_device(ctx.handle, C.byref(sh), bbox.ctypes.data, 1, 512,
-                                                                             g512.data_ptr())), 10)
-            other["config2_dense_512cube_de_grid_one_span"] = {"ms": ms2, "samples_per_s": 513 ** 3 / (ms2 * 1e-3)}
-            del g512, m1
+                   "api": "ctc_mesh_spans (host pointers; pinned host buffers)", "steps": args.steps}
+            # ---- parity gate + CPU baseline: ONE oracle run over the whole volume serves both -----------------
+            if not args.no_cpu:
+                ora = oracle_volume(spans)
+                planes = cb.sample_signs(spans, shape, RES, ctx)
+                gv = v_host.numpy().view(np.uint8).reshape(-1)[: nv * 28].view(cb.VERTEX_DTYPE)
+                parity = parity_gate(gv, i_host.numpy().view(np.uint32)[:ni], v_off, i_off, planes, ora, spans, exact=not fast)
+                parity["mode"] = "fast" if fast else "exact"
+                parity["checked"] = "the e2e leg's host buffers (ctc_mesh_spans) and ctc_sample_signs against the CPU oracle, all spans"
+                cpu = {"value": ora["samples"] / ora["secs"], "unit": UNIT, "cores": ora["threads"], "kind": "port",
+                       "sample": f"all {ora['spans']} spans of the volume, {ora['secs']:.2f} s", "span_meshes_per_s": ora["spans"] / ora["secs"]}
+                del ora, planes
+            del v_host, i_host
+        # ---- the other BASELINE.json configs and small batches (N = 1; their parity lives in tests/) --------------
+        other, small = None, None
+        if world == 1 and args.tiles == TILES and not args.no_other:
+            other, small = other_configs(ctx, cb, _lib, refine, torch, device, stream, DeviceMesher, nominal, sms.value or 148, sm_max)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.tiles == TILES else f"bbox_as_{args.tiles}^3_spans_R64",
-                       "spans": int(nspans), "spans_per_gpu": int(len(mine)), "resolution": RES, "power": POWER, "max_iters": MAX_ITERS,
-                       "bailout": BAILOUT, "math": "fast" if fast else "exact",
-                       "parallelism": ((f"{world} volume(s) of {len(mine)} spans, one per rank (weak scaling), meshes gathered to rank 0" if not strong
-                                        else f"one volume of {nspans} spans dealt round-robin over {world} rank(s) (strong scaling), meshes gathered to rank 0")
-                                       + ("" if world == 1 else (" by one-sided puts into rank 0's IPC-mapped buffers (copy engines "
-                                          "over NVLink, pipelined behind compute)" if args.gather == "peer"
-                                          else " by grouped NCCL send/recv"))),
-                       "l2": "per-step working set (4.5 GB of sample grids streamed in 512 MiB launch groups + 0.7 GB of "
-                             "mesh per volume) exceeds the 126 MB L2; no explicit flush"},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": bench_config(world),
+            "details": {"math": "fast (sign-exact: suspects re-evaluated with the exact arithmetic)" if fast else "exact",
+                        "spans_per_gpu": int(info["mine"]),
+                        "parallelism": (f"{world} volume(s) of {info['mine']} spans, one per rank (weak scaling), meshes gathered to rank 0"
+                                        + ("" if world == 1 else (" by one-sided puts into rank 0's IPC-mapped buffers (copy engines over "
+                                           "NVLink, pipelined behind compute)" if args.gather == "peer" else " by grouped NCCL send/recv"))),
+                        "index_wire": "packed 8-byte quads, widened on rank 0" if info["packed"] else "six u32 per quad"},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
-            "vertices": nv_tot, "indices": ni_tot, "gathered_bytes_per_step": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (8 / 6 if use_packed else 4)),
+            "vertices": info["nv_tot"], "indices": info["ni_tot"], "gathered_bytes_per_step": info["gathered_bytes"],
             "gpu_launches": int(launches2 - launches1),
-            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "other_configs": other,
+            "clocks": clocks, "roofline": roofline, "roofline_extraction": roofline_extraction, "whole_step": whole,
+            "parity": parity, "e2e": e2e, "cpu_baseline": cpu, "strong_scaling": strong, "other_configs": other,
+            "small_batches": small,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -579,21 +623,112 @@ def ours_main(args):
     return 0
 
 
+def other_configs(ctx, cb, _lib, refine, torch, device, stream, DeviceMesher, nominal_tf, sms, sm_max_mhz):
+    """BASELINE configs 1-4 (device-resident, fast mode unless stated) and the latency of small host-buffer calls."""
+    L = _lib.lib()
+    n3 = (RES + 1) ** 3
+    shape = cb.Mandelbulb.classic(MAX_ITERS, BAILOUT, fast=True)
+    sh = shape._ctc_shape()
+    out = {}
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    # config 1: the 64 startup leaves (mesh/mod.rs:52-56)
+    startup = cb.spans_array([n.span for n in cb.startup_tree(shape.bounding_box()).leaves()])
+    m1 = DeviceMesher(ctx, torch, device, 700_000, 4_200_000, 64)
+    ms1 = timed(lambda: (m1.launch(sh, startup, RES), m1.result()), 20)
+    out["config1_startup_octree_64_spans_R64"] = {"ms": ms1, "samples_per_s": 64 * n3 / (ms1 * 1e-3), "span_meshes_per_s": 64 / (ms1 * 1e-3)}
+    # config 2: dense 512^3 DE sample grid, one bbox span (pass 1 only: meshing this span panics in the reference)
+    bbox = np.array([[-1.2, -1.2, -1.2, 1.2, 1.2, 1.2]], dtype=np.float32)
+    g512 = torch.empty((513 ** 3,), dtype=torch.float32, device=device)
+    ms2 = timed(lambda: ctx.check(L.ctc_sample_grids_device(ctx.handle, C.byref(sh), bbox.ctypes.data, 1, 512, g512.data_ptr())), 10)
+    out["config2_dense_512cube_de_grid_one_span"] = {"ms": ms2, "samples_per_s": 513 ** 3 / (ms2 * 1e-3)}
+    del g512, m1
+    # config 3: the octree refined to depth 6 around the default-orbit camera, every leaf at R = 64
+    leaves, _ = refine.config3_spans(cb.Mandelbulb.classic(MAX_ITERS, BAILOUT), 6, ctx)
+    m3 = DeviceMesher(ctx, torch, device, 2_500_000, 15_000_000, len(leaves))
+    ms3 = timed(lambda: (m3.launch(sh, leaves, RES), m3.result()), 10)
+    nv3, ni3, _ = m3.result()
+    out["config3_depth6_refinement"] = {"leaves": int(len(leaves)), "ms": ms3, "samples_per_s": len(leaves) * n3 / (ms3 * 1e-3),
+                                        "span_meshes_per_s": len(leaves) / (ms3 * 1e-3), "vertices": nv3, "quads": ni3 // 6}
+    del m3
+    # config 4: power sweep over the 1024^3 volume (4096 spans), 32 and 128 iterations.  P = 8 runs the polynomial
+    # (FMA-pipe) step; P = 2, 4, 16 the generic step, whose fast form is trig-free (complex binary powers), so its
+    # transcendental load is 3 MUFU per iteration (rsqrt, sqrt, and the epilogue's lg2/sqrt/rcp once per sample).
+    tiles = workload_spans(TILES)
+    m4 = DeviceMesher(ctx, torch, device, 40_000_000, 240_000_000, len(tiles))
+    xu_peak = sms * 16 * sm_max_mhz * 1e6          # MUFU results per second (16 lanes per SM)
+    cells = {}
+    stats = (C.c_uint64 * 3)()
+    for power in (2, 4, 8, 16):
+        for iters in (32, 128):
+            s4 = cb.Mandelbulb(power, iters, BAILOUT, fast=True)._ctc_shape()
+            ms4 = timed(lambda: (m4.launch(s4, tiles, RES), m4.result(allow_lerp_assert=True)), 2)
+            nv4, ni4, t4 = m4.result(allow_lerp_assert=True)
+            sub = np.ascontiguousarray(tiles[::16])                  # iteration statistics on every 16th span
+            ctx.check(L.ctc_iteration_stats(ctx.handle, C.byref(s4), sub.ctypes.data, sub.shape[0], RES, stats))
+            k_mean = int(stats[0]) / max(int(stats[2]), 1)
+            samples = len(tiles) * n3
+            mufu = samples * (2.0 * k_mean + 3.0)                    # per completed iteration: rsqrt + sqrt; epilogue: lg2, sqrt, rcp
+            cell = {"ms": ms4, "samples_per_s": samples / (ms4 * 1e-3), "span_meshes_per_s": len(tiles) / (ms4 * 1e-3),
+                    "vertices": nv4, "quads": ni4 // 6, "mean_iterations_per_sample": k_mean,
+                    "pass_ms": {"first_de": t4.first_ms, "second": t4.second_ms, "third": t4.third_ms},
+                    "mufu_ops_pass1": mufu, "xu_frac_pass1": mufu / (t4.first_ms * 1e-3) / xu_peak if t4.first_ms > 0 else None}
+            if power == 8:
+                fl = FLOPS_PER_ITERATION * k_mean * samples + FLOPS_FIXED * samples
+                cell["pass1_tflops_algorithmic"] = fl / (t4.first_ms * 1e-3) / 1e12 if t4.first_ms > 0 else None
+                cell["pass1_frac_of_nominal_fp32"] = cell["pass1_tflops_algorithmic"] / nominal_tf if cell["pass1_tflops_algorithmic"] else None
+            cells[f"p{power}_i{iters}"] = cell
+    out["config4_power_sweep_1024cube"] = {"cells": cells, "xu_peak_mufu_per_s": xu_peak,
+                                           "note": "fast mode; pass times of the overlapped run (pass 1 shares the SMs with the previous "
+                                                   "group's extraction); iteration means from every 16th span"}
+    del m4
+    torch.cuda.empty_cache()
+    # small batches: the drop-in's steady state (64 leaves at start, 8 per split): host buffers, wall clock per call
+    small = {}
+    v = np.empty(400_000, dtype=cb.VERTEX_DTYPE); idx = np.empty(2_400_000, dtype=np.uint32)
+    for n in (1, 8, 64):
+        sp = np.ascontiguousarray(startup[20:20 + n] if n < 64 else startup)
+        v_off = np.zeros(n + 1, dtype=np.uint64); i_off = np.zeros(n + 1, dtype=np.uint64)
+        tt = _lib.CtcTimings()
+
+        def call():
+            ctx.check(L.ctc_mesh_spans(ctx.handle, C.byref(sh), sp.ctypes.data, n, RES, v.ctypes.data, len(v), idx.ctypes.data, len(idx),
+                                       v_off.ctypes.data, i_off.ctypes.data, C.byref(tt)))
+        for _ in range(5):
+            call()
+        t0 = time.perf_counter()
+        reps = 50
+        for _ in range(reps):
+            call()
+        wall = (time.perf_counter() - t0) / reps
+        small[f"{n}_spans"] = {"wall_us_per_call": wall * 1e6, "device_us_kernels": (tt.first_ms + tt.second_ms + tt.third_ms) * 1e3,
+                               "vertices": int(v_off[n]), "api": "ctc_mesh_spans, pageable host buffers"}
+    return out, small
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic instead of the fast mode")
+    ap.add_argument("--exact", action="store_true", help="bit-exact arithmetic instead of the (sign-exact) fast mode")
     ap.add_argument("--tiles", type=int, default=TILES, help="tiles per axis (default 16 -> the 1024^3 workload)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle run (parity gate + cpu_baseline)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (BASELINE config 5)")
+    ap.add_argument("--no-other", action="store_true", help="skip other_configs / small_batches")
+    ap.add_argument("--strong-steps", type=int, default=3, help="timed steps of the strong-scaling leg")
     ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
     ap.add_argument("--wire-packed", action="store_true", help="N>1: force packed quad records (default only for N > 4)")
     ap.add_argument("--wire-u32", action="store_true",
                     help="N>1, --gather peer: ship six u32 indices per quad instead of packed 8-byte quad records")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: one volume per rank (weak, default) or one volume sharded over all ranks (strong)")
     ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],
                     help="N>1: copy-engine puts into rank 0's IPC-mapped buffers (default), kernels storing "
                          "straight into them (direct), or NCCL send/recv")

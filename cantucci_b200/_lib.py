@@ -69,6 +69,7 @@ EXPORTS = (
     "ctc_ray_march", "ctc_device_alloc", "ctc_device_free", "ctc_ipc_export", "ctc_ipc_open", "ctc_ipc_close",
     "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
     "ctc_ctx_set_fast_band", "ctc_mesh_fixups", "ctc_fast_sign_probe", "ctc_sample_signs",
+    "ctc_ctx_set_kernel_timing", "ctc_mesh_kernel_times", "ctc_iteration_stats_points",
     "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
     "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
 )
@@ -129,6 +130,8 @@ def lib() -> C.CDLL:
     L.ctc_mesh_result.argtypes = [vp, u64p, u64p, C.POINTER(CtcTimings)]
     L.ctc_iteration_stats.restype = C.c_int
     L.ctc_iteration_stats.argtypes = [vp, shp, spn, sz, u32, u64p]
+    L.ctc_iteration_stats_points.restype = C.c_int
+    L.ctc_iteration_stats_points.argtypes = [vp, shp, vp, sz, u64p]
     L.ctc_ray_march.restype = C.c_int
     L.ctc_ray_march.argtypes = [vp, shp, vp, vp, sz, u32, C.c_float, vp, vp]
     L.ctc_device_alloc.restype = C.c_int
@@ -157,6 +160,10 @@ def lib() -> C.CDLL:
     L.ctc_sample_signs.argtypes = [vp, shp, spn, sz, u32, vp]
     L.ctc_fast_sign_probe.restype = C.c_int
     L.ctc_fast_sign_probe.argtypes = [vp, shp, spn, sz, u32, u64p, sz]
+    L.ctc_ctx_set_kernel_timing.restype = C.c_int
+    L.ctc_ctx_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.ctc_mesh_kernel_times.restype = C.c_int
+    L.ctc_mesh_kernel_times.argtypes = [vp, C.POINTER(C.c_double), sz]
     L.ctc_last_error_copy.restype = C.c_size_t
     L.ctc_last_error_copy.argtypes = [vp, C.c_char_p, sz]
     L.ctc_multi_create.restype = C.c_int
@@ -216,6 +223,17 @@ class Context:
 
     def synchronize(self):
         self.check(lib().ctc_ctx_synchronize(self._h))
+
+    KERNELS = ("sample_grids", "fixup_suspects", "classify", "scan_chunks", "apply_prefix", "vertex", "quads")
+
+    def set_kernel_timing(self, enable: bool):
+        self.check(lib().ctc_ctx_set_kernel_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self) -> dict:
+        """Device ms per kernel of the last fetched mesh call (needs set_kernel_timing(True))."""
+        ms = (C.c_double * 8)()
+        self.check(lib().ctc_mesh_kernel_times(self._h, ms, 8))
+        return {name: float(ms[k]) for k, name in enumerate(self.KERNELS)}
 
     def set_fast_band(self, kappa: float = 0.0):
         """Fast mode's sign-trust band (0 = the calibrated default)."""

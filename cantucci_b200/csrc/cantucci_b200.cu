@@ -66,6 +66,8 @@ struct ctc_ctx {
     uint64_t launches = 0;
     uint32_t group_spans = 0;   // 0 = auto
     bool timing = true;
+    bool kernel_timing = false; // ctc_ctx_set_kernel_timing: an event pair around every kernel (measurement runs)
+    double kernel_ms[CTC_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool overlap = true;        // ctc_ctx_set_overlap
     bool wire_quads = false;    // ctc_ctx_set_index_wire: ctc_mesh_spans delivers packed 8-byte quad records
     // fast mode's sign-trust band (de_device.cuh, fast_suspect_*); calibrated by ctc_fast_sign_probe
@@ -238,10 +240,11 @@ cudaEvent_t take_event(ctc_ctx* ctx) {
     return ctx->ev_pool[ctx->ev_used++];
 }
 
+// pass ids 0..2 = the reference's three passes (always timed); 3 + k = kernel k (only with kernel_timing)
 struct PassTimer {
     ctc_ctx* ctx; int pass; cudaStream_t st; cudaEvent_t a = nullptr;
     PassTimer(ctc_ctx* c, int p, cudaStream_t s) : ctx(c), pass(p), st(s) {
-        if (ctx->timing) { a = take_event(ctx); if (a) cudaEventRecord(a, st); }
+        if (p < 3 ? ctx->timing : ctx->kernel_timing) { a = take_event(ctx); if (a) cudaEventRecord(a, st); }
     }
     ~PassTimer() {
         if (a) { cudaEvent_t b = take_event(ctx); if (b) { cudaEventRecord(b, st); ctx->ev_pairs.push_back({a, b, pass}); } }
@@ -503,6 +506,7 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
             PassTimer t(ctx, 0, sA);
             CK(cudaMemsetAsync(sign_bits, 0, (size_t)cnt * sign_stride * 4, sA));
             if (listed) CK(cudaMemsetAsync(sl.count, 0, sizeof(unsigned int), sA));
+            PassTimer k(ctx, 3 + CTC_K_SAMPLE_GRIDS, sA);
 #define CALL(F, V) launch_sample<F, V>(ctx, sh, geom, R, lg, grids, gp.n3, cnt, gp.n3, sign_bits, sign_stride, sl, sA)
             DISPATCH(fast, variant, CALL);
 #undef CALL
@@ -514,19 +518,32 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         dim3 cgrid(gp.chunks_per_span, cnt);
         {   // pass 2: (fast mode: sign repair,) classify, scan, vertices
             PassTimer t(ctx, 1, sE);
-            if (listed) launch_fixup(ctx, sh, variant, geom, R, grids, gp.n3, sign_bits, sign_stride, sl, st, sE);
-            classify_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
-                                                                gp.chunk_words, m, ctx->chunk_counts.as<uint2>());
-            scan_chunks_kernel<<<1, kScanThreads, 0, sE>>>(
-                ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
-                (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
-                reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st,
-                pipeline ? ctx->progress_d + 2 * gi : nullptr);
-            apply_prefix_kernel<<<cgrid, kThreads, 0, sE>>>(m, ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), gp.words_per_span,
-                                                                    gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
-                                                                    ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
-                                                                    cell_cap);
+            if (listed) {
+                PassTimer k(ctx, 3 + CTC_K_FIXUP, sE);
+                launch_fixup(ctx, sh, variant, geom, R, grids, gp.n3, sign_bits, sign_stride, sl, st, sE);
+            }
+            {
+                PassTimer k(ctx, 3 + CTC_K_CLASSIFY, sE);
+                classify_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
+                                                            gp.chunk_words, m, ctx->chunk_counts.as<uint2>());
+            }
+            {
+                PassTimer k(ctx, 3 + CTC_K_SCAN, sE);
+                scan_chunks_kernel<<<1, kScanThreads, 0, sE>>>(
+                    ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
+                    (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
+                    reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st,
+                    pipeline ? ctx->progress_d + 2 * gi : nullptr);
+            }
+            {
+                PassTimer k(ctx, 3 + CTC_K_PREFIX, sE);
+                apply_prefix_kernel<<<cgrid, kThreads, 0, sE>>>(m, ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), gp.words_per_span,
+                                                                gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
+                                                                ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
+                                                                cell_cap);
+            }
             ctx->launches += 3;
+            PassTimer k(ctx, 3 + CTC_K_VERTEX, sE);
 #define CALL(F, V) launch_vertex<F, V>(ctx, sh, geom, grids, gp.n3, R, lg, ctx->cell_of.as<uint32_t>(), cell_cap, st, \
                                        (uint32_t)s0, reinterpret_cast<float*>(d_v), (unsigned long long)vcap, vblocks, sE)
             DISPATCH(fast, variant, CALL);
@@ -568,14 +585,18 @@ int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ct
     const MeshState* st = static_cast<const MeshState*>(ctx->h_state.p);
     if (n_vertices) *n_vertices = st->total_v;
     if (n_indices) *n_indices = 6ull * st->total_q;
-    if (timings) {
-        double ms[3] = {0, 0, 0};
+    if (timings || ctx->kernel_timing) {
+        double ms[3 + CTC_NUM_KERNELS] = {0};
         for (const EventPair& p : ctx->ev_pairs) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) ms[p.pass] += t;
         }
-        timings->first_ms = ms[0]; timings->second_ms = ms[1]; timings->third_ms = ms[2];
-        timings->vertices = st->total_v; timings->faces = st->total_q;
+        if (timings) {
+            timings->first_ms = ms[0]; timings->second_ms = ms[1]; timings->third_ms = ms[2];
+            timings->vertices = st->total_v; timings->faces = st->total_q;
+        }
+        for (int k = 0; k < CTC_NUM_KERNELS; ++k) ctx->kernel_ms[k] = ms[3 + k];
+        ctx->kernel_ms[CTC_K_QUADS] = ms[2];      // pass 3 is one kernel
     }
     // A truncated output is reported ahead of the lerp assert ("mesh still delivered" must not hide a
     // mesh that is NOT all there); the assert's span stays readable in the message either way.
@@ -659,6 +680,20 @@ int ctc_ctx_set_group_spans(ctc_ctx* ctx, uint32_t spans_per_group) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->group_spans = spans_per_group;
+    return CTC_OK;
+}
+
+int ctc_ctx_set_kernel_timing(ctc_ctx* ctx, int enable) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->kernel_timing = enable != 0;
+    return CTC_OK;
+}
+
+int ctc_mesh_kernel_times(ctc_ctx* ctx, double* ms, size_t n) {
+    if (!ctx || !ms) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (size_t k = 0; k < n; ++k) ms[k] = k < (size_t)CTC_NUM_KERNELS ? ctx->kernel_ms[k] : 0.0;
     return CTC_OK;
 }
 
@@ -973,6 +1008,32 @@ int ctc_iteration_stats(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* sp
         else iteration_stats_kernel<kVarSphere><<<grid, kThreads, 0, ctx->stream>>>(sh, geom, resolution, lg, inv_r, o);
         ctx->launches++;
     }
+    CK(cudaGetLastError());
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, ctx->pts_out.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    return CTC_OK;
+}
+
+int ctc_iteration_stats_points(ctc_ctx* ctx, const ctc_shape* shape, const float* d_xyz, size_t n, uint64_t out[3]) {
+    if (!ctx || !out) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ShapeDev sh;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    out[0] = out[1] = out[2] = 0;
+    if (n == 0) return CTC_OK;
+    if (!d_xyz) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL point buffer");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->pts_out.ensure(3 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->pts_out.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+    unsigned long long* o = ctx->pts_out.as<unsigned long long>();
+    const int variant = shape_variant(shape);
+    if (variant == kVarP8) iteration_stats_points_kernel<kVarP8><<<blocks, kThreads, 0, ctx->stream>>>(sh, d_xyz, n, o);
+    else if (variant == kVarGeneric) iteration_stats_points_kernel<kVarGeneric><<<blocks, kThreads, 0, ctx->stream>>>(sh, d_xyz, n, o);
+    else iteration_stats_points_kernel<kVarSphere><<<blocks, kThreads, 0, ctx->stream>>>(sh, d_xyz, n, o);
+    ctx->launches++;
     CK(cudaGetLastError());
     unsigned long long h[3];
     CK(cudaMemcpyAsync(h, ctx->pts_out.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));

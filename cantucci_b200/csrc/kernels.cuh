@@ -835,6 +835,33 @@ iteration_stats_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t 
     }
 }
 
+// The same statistics for a point list (packed xyz): the algorithmic flops of pass 2's 7 DE evaluations
+// per vertex.
+template <int kVariant>
+__global__ void __launch_bounds__(kThreads)
+iteration_stats_points_kernel(ShapeDev sh, const float* __restrict__ xyz, size_t n, unsigned long long* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    uint32_t k = 0, bailed = 0, cnt = 0;
+    if (i < n) {
+        if (kVariant != kVarSphere) {
+            (void)mandelbulb_de_exact<kVariant == kVarP8>(sh, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &k);
+            bailed = k < sh.max_iters;
+        }
+        cnt = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k += __shfl_xor_sync(0xffffffffu, k, o);
+        bailed += __shfl_xor_sync(0xffffffffu, bailed, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(&out[0], (unsigned long long)k);
+        atomicAdd(&out[1], (unsigned long long)bailed);
+        atomicAdd(&out[2], (unsigned long long)cnt);
+    }
+}
+
 // Calibration of the sign-trust band (fast_suspect_*, de_device.cuh): every sample of the span batch is
 // evaluated by the fast path (raw, no repair) AND by the exact path.  out[] (unsigned long long):
 //   [0] samples                      [1] raw sign mismatches fast vs exact

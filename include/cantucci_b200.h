@@ -118,6 +118,14 @@ CTC_API int ctc_ctx_set_group_spans(ctc_ctx *ctx, uint32_t spans_per_group);
  * priority stream concurrently with the next group's DE kernel.  0: strictly
  * serial kernels (per-pass timings then do not overlap; used for profiling). */
 CTC_API int ctc_ctx_set_overlap(ctc_ctx *ctx, int enable);
+/* Measurement runs: 1 = an event pair around EVERY kernel of the following mesh calls (off by default:
+ * the three pass timers are always on).  ctc_mesh_kernel_times then returns, for the last call whose
+ * result was fetched, the device milliseconds per kernel summed over the launch groups (index CTC_K_*).
+ * Meaningful per kernel only with ctc_ctx_set_overlap(0); with overlap on they share the SMs. */
+enum { CTC_K_SAMPLE_GRIDS = 0, CTC_K_FIXUP = 1, CTC_K_CLASSIFY = 2, CTC_K_SCAN = 3, CTC_K_PREFIX = 4,
+       CTC_K_VERTEX = 5, CTC_K_QUADS = 6, CTC_NUM_KERNELS = 8 };
+CTC_API int ctc_ctx_set_kernel_timing(ctc_ctx *ctx, int enable);
+CTC_API int ctc_mesh_kernel_times(ctc_ctx *ctx, double *ms, size_t n);
 CTC_API int ctc_ctx_synchronize(ctc_ctx *ctx);
 /* Human-readable description of the last failure on this context.  The pointer stays valid until the
  * next failing call on the context: with several threads on ONE context use ctc_last_error_copy, which
@@ -282,6 +290,10 @@ CTC_API int ctc_sample_signs(ctc_ctx *ctx, const ctc_shape *shape, const ctc_spa
 CTC_API int ctc_fast_sign_probe(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
                                 uint32_t resolution, uint64_t *out, size_t out_words);
 
+/* The same statistics for n packed xyz points in DEVICE memory (the 7 evaluation points per vertex of
+ * pass 2, for its algorithmic flop count). */
+CTC_API int ctc_iteration_stats_points(ctc_ctx *ctx, const ctc_shape *shape, const float *d_xyz, size_t n,
+                                       uint64_t out[3]);
 /* Sustained FP32 FMA rate of the device in TFLOP/s (FMA = 2 flops), measured
  * with dependent-free FFMA streams on every SM. */
 CTC_API int ctc_fp32_peak_probe(ctc_ctx *ctx, double *tflops, int *num_sms);

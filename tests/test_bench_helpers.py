@@ -1,4 +1,4 @@
-"""CPU checks of bench.py's host-side helpers (no GPU): the bounded CPU sample and the clock parser."""
+"""CPU checks of bench.py's host-side helpers (no GPU): the workload, the parity gate and the clock parser."""
 import os
 import sys
 
@@ -8,18 +8,34 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
 
-def test_cpu_sample_is_a_quarter_of_the_volume_spread_over_all_tile_coordinates():
+def test_workload_tiles_cover_the_bounding_box_and_both_arms_print_one_config():
     spans = bench.workload_spans(16)
     assert spans.shape == (4096, 6)
-    sample = bench.cpu_sample_spans(spans, 4)
-    assert sample.shape == (1024, 6)
-    # every x, y and z tile coordinate of the 16^3 tiling is visited
-    for axis in range(3):
-        assert len(np.unique(sample[:, axis])) == 16
     # tiles share faces exactly and cover the bounding box
     assert np.isclose(spans[:, :3].min(), -1.2) and np.isclose(spans[:, 3:].max(), 1.2)
     vol = np.prod((spans[:, 3:] - spans[:, :3]).astype(np.float64), axis=1).sum()
     assert abs(vol - 2.4 ** 3) < 1e-4
+    c1, c8 = bench.bench_config(1), bench.bench_config(8)
+    assert c1["spans"] == 4096 and c8["spans"] == 8 * 4096 and c1.keys() == c8.keys()
+    assert c1["samples_per_step"] == 4096 * 65 ** 3
+
+
+def test_parity_gate_accepts_the_oracle_and_flags_a_flipped_sign_or_a_moved_vertex():
+    """The gate itself, on the CPU: the oracle against itself is clean (exact tolerances), one flipped
+    sign bit or one moved vertex is reported."""
+    spans = np.ascontiguousarray(bench.workload_spans(16)[1900:1932])
+    ora = bench.oracle_volume(spans)
+    u64 = lambda a: a.astype(np.uint64)
+    ok = bench.parity_gate(ora["v"].copy(), ora["i"].copy(), u64(ora["v_off"]), u64(ora["i_off"]), ora["planes"].copy(), ora, spans, exact=True)
+    assert ok["ok"] and ok["sign_mismatches"] == 0 and ok["index_buffers_identical"] and ok["vertex_records_bit_identical"]
+    assert ok["indices_sha256"] == ok["indices_sha256_reference"] and ok["vertices"] == len(ora["v"]) > 1000
+    planes = ora["planes"].copy(); planes[3, 100] ^= 4
+    bad = bench.parity_gate(ora["v"].copy(), ora["i"].copy(), u64(ora["v_off"]), u64(ora["i_off"]), planes, ora, spans, exact=False)
+    assert not bad["ok"] and bad["sign_mismatches"] == 1 and bad["spans_with_sign_mismatch"] == 1
+    v = ora["v"].copy(); v["position"][5, 0] += 1e-6
+    moved = bench.parity_gate(v, ora["i"].copy(), u64(ora["v_off"]), u64(ora["i_off"]), ora["planes"].copy(), ora, spans, exact=True)
+    assert not moved["ok"] and not moved["vertex_records_bit_identical"] and moved["position_err_cells_max"] > 0
+    assert bench.parity_gate(v, ora["i"].copy(), u64(ora["v_off"]), u64(ora["i_off"]), ora["planes"].copy(), ora, spans, exact=False)["ok"]
 
 
 def test_clock_sampler_summarises_rows_inside_the_timed_region():
