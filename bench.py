@@ -325,7 +325,7 @@ def ours_main(args):
         probe = DeviceMesher(ctx, torch, device, 1, 6, len(local_spans))
         probe.launch(sh, local_spans, RES)
         rc, nv, ni, _ = probe.result_status()
-        if rc not in (_lib.CTC_OK, _lib.CTC_ERR_OVERFLOW):
+        if rc not in (_lib.CTC_OK, _lib.CTC_ERR_OVERFLOW, _lib.CTC_ERR_LERP_ASSERT):
             ctx.check(rc)
         max_span_v = int(probe.v_off[: len(local_spans) + 1].diff().max()) if len(local_spans) else 0
         return nv, ni, max_span_v
@@ -360,10 +360,10 @@ def ours_main(args):
                 "gathered_bytes": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (8 / 6 if use_packed else 4))}
         return sched, local, info
 
-    def run_step(sched, spans, local):
+    def run_step(sched, spans, local, allow_lerp_assert=False):
         if isinstance(sched, PeerGatherScheduler):
-            return sched.run(sh, spans, RES, local=local)
-        return sched.run(sh, spans, RES)
+            return sched.run(sh, spans, RES, local=local, allow_lerp_assert=allow_lerp_assert)
+        return sched.run(sh, spans, RES, allow_lerp_assert=allow_lerp_assert)
 
     def timed_steps(fn, steps):
         """`steps` calls of fn between CUDA events on the launching stream, barrier + sync on both sides;
@@ -417,7 +417,9 @@ def ours_main(args):
     if not args.no_strong and args.tiles == TILES:
         vol5 = workload_spans(64)                          # the 4096^3 volume as 64^3 spans of R = 64: 262 144 spans
         sched5, local5, info5 = make_scheduler(vol5, "interleave", args.gather, wire_packed_from=5)
-        step5 = lambda: run_step(sched5, vol5, local5)
+        # (a few of the 262 144 spans carry NaN samples next to the surface: the reference's worker would panic
+        # there, math.rs:19, and lose that one job; the C ABI reports CTC_ERR_LERP_ASSERT and still delivers)
+        step5 = lambda: run_step(sched5, vol5, local5, allow_lerp_assert=True)
         step5()
         ms5 = timed_steps(step5, args.strong_steps)
         L.ctc_mesh_result(ctx.handle, None, None, C.byref(t))
@@ -671,7 +673,8 @@ def other_configs(ctx, cb, _lib, refine, torch, device, stream, DeviceMesher, no
             s4 = cb.Mandelbulb(power, iters, BAILOUT, fast=True)._ctc_shape()
             ms4 = timed(lambda: (m4.launch(s4, tiles, RES), m4.result(allow_lerp_assert=True)), 2)
             nv4, ni4, t4 = m4.result(allow_lerp_assert=True)
-            sub = np.ascontiguousarray(tiles[::16])                  # iteration statistics on every 16th span
+            ti = np.arange(len(tiles))                               # iteration statistics on 1/16 of the spans, spread evenly
+            sub = np.ascontiguousarray(tiles[((ti // 256) + 3 * ((ti // 16) % 16) + 5 * (ti % 16)) % 16 == 0])
             ctx.check(L.ctc_iteration_stats(ctx.handle, C.byref(s4), sub.ctypes.data, sub.shape[0], RES, stats))
             k_mean = int(stats[0]) / max(int(stats[2]), 1)
             samples = len(tiles) * n3
@@ -687,12 +690,12 @@ def other_configs(ctx, cb, _lib, refine, torch, device, stream, DeviceMesher, no
             cells[f"p{power}_i{iters}"] = cell
     out["config4_power_sweep_1024cube"] = {"cells": cells, "xu_peak_mufu_per_s": xu_peak,
                                            "note": "fast mode; pass times of the overlapped run (pass 1 shares the SMs with the previous "
-                                                   "group's extraction); iteration means from every 16th span"}
+                                                   "group's extraction); iteration means from 1/16 of the spans, spread evenly through the volume"}
     del m4
     torch.cuda.empty_cache()
     # small batches: the drop-in's steady state (64 leaves at start, 8 per split): host buffers, wall clock per call
     small = {}
-    v = np.empty(400_000, dtype=cb.VERTEX_DTYPE); idx = np.empty(2_400_000, dtype=np.uint32)
+    v = np.empty(700_000, dtype=cb.VERTEX_DTYPE); idx = np.empty(4_200_000, dtype=np.uint32)
     for n in (1, 8, 64):
         sp = np.ascontiguousarray(startup[20:20 + n] if n < 64 else startup)
         v_off = np.zeros(n + 1, dtype=np.uint64); i_off = np.zeros(n + 1, dtype=np.uint64)

@@ -70,6 +70,7 @@ EXPORTS = (
     "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
     "ctc_ctx_set_fast_band", "ctc_mesh_fixups", "ctc_fast_sign_probe", "ctc_sample_signs",
     "ctc_ctx_set_kernel_timing", "ctc_mesh_kernel_times", "ctc_iteration_stats_points",
+    "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats",
     "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
     "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
 )
@@ -160,6 +161,10 @@ def lib() -> C.CDLL:
     L.ctc_sample_signs.argtypes = [vp, shp, spn, sz, u32, vp]
     L.ctc_fast_sign_probe.restype = C.c_int
     L.ctc_fast_sign_probe.argtypes = [vp, shp, spn, sz, u32, u64p, sz]
+    L.ctc_ctx_set_coalescing.restype = C.c_int
+    L.ctc_ctx_set_coalescing.argtypes = [vp, C.c_int]
+    L.ctc_ctx_coalescing_stats.restype = C.c_int
+    L.ctc_ctx_coalescing_stats.argtypes = [vp, u64p, u64p]
     L.ctc_ctx_set_kernel_timing.restype = C.c_int
     L.ctc_ctx_set_kernel_timing.argtypes = [vp, C.c_int]
     L.ctc_mesh_kernel_times.restype = C.c_int
@@ -225,6 +230,15 @@ class Context:
         self.check(lib().ctc_ctx_synchronize(self._h))
 
     KERNELS = ("sample_grids", "fixup_suspects", "classify", "scan_chunks", "apply_prefix", "vertex", "quads")
+
+    def set_coalescing(self, enable: bool):
+        self.check(lib().ctc_ctx_set_coalescing(self._h, 1 if enable else 0))
+
+    def coalescing_stats(self) -> tuple[int, int]:
+        """(batched launches so far, requests they served)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.check(lib().ctc_ctx_coalescing_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def set_kernel_timing(self, enable: bool):
         self.check(lib().ctc_ctx_set_kernel_timing(self._h, 1 if enable else 0))

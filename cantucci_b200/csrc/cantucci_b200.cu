@@ -56,6 +56,8 @@ constexpr float kDefaultKappa = 1.0f / 262144.0f;   // 2^-18
 
 }  // namespace
 
+struct MeshRequest;
+
 struct ctc_ctx {
     int device = 0;
     int num_sms = 148;
@@ -63,6 +65,18 @@ struct ctc_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     std::string err;
+    // submission queue of the host-pointer mesh call: concurrent callers (the reference meshes one leaf per
+    // thread-pool job, mesh/mod.rs:141-148) are coalesced into batched launches by whichever caller leads
+    std::mutex q_mu;
+    std::condition_variable q_cv;
+    std::vector<MeshRequest*> q;
+    bool q_leader = false;
+    bool coalesce = true;       // ctc_ctx_set_coalescing
+    uint64_t batches = 0, batched_requests = 0;
+    std::vector<ctc_span> b_spans;                 // staging of a coalesced batch
+    std::vector<uint64_t> b_voff, b_ioff;
+    PinnedBuf b_v, b_i;
+    bool async_inflight = false;   // an asynchronous (device-pointer) call may still be using the staging buffers
     uint64_t launches = 0;
     uint32_t group_spans = 0;   // 0 = auto
     bool timing = true;
@@ -72,7 +86,6 @@ struct ctc_ctx {
     bool wire_quads = false;    // ctc_ctx_set_index_wire: ctc_mesh_spans delivers packed 8-byte quad records
     // fast mode's sign-trust band (de_device.cuh, fast_suspect_*); calibrated by ctc_fast_sign_probe
     float kappa = kDefaultKappa;
-    bool kappa_user = false;    // set by ctc_ctx_set_fast_band: used as given, whatever max_iters
 
     // workspace
     DevBuf suspects, suspect_count;               // fast mode: K1's suspect lists (double-buffered like the grids)
@@ -138,15 +151,12 @@ int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
         d.max_iters = s->max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s->max_iters;
         d.bailout = s->bailout;
         { volatile float b2 = s->bailout * s->bailout; d.bail2 = b2; }
-        // The band is calibrated for orbits of up to ~12 iterations (every BASELINE config with the default
-        // (6, 2.5)); longer orbits are chaotic near the surface and the first-order bound loosens by a constant
-        // per iteration, so the default band doubles every 4 further iterations (up to 2^6): profiles/sign_probe_r2.md.
-        float kappa = ctx ? ctx->kappa : kDefaultKappa;
-        if (!ctx || !ctx->kappa_user) {
-            uint64_t extra = s->max_iters > 8 ? (s->max_iters - 8 + 3) / 4 : 0;
-            if (extra > 6) extra = 6;
-            kappa *= (float)(1u << extra);
-        }
+        // The band is calibrated on orbits of up to 12 iterations (every BASELINE config with the default
+        // (6, 2.5): zero sign mismatches over 1.1 G samples with an 8x margin).  Longer orbits are chaotic near
+        // the surface -- a 1-ulp change of the input moves the reference's own result by O(1) there -- and the
+        // same band leaves ~1e-7 (32 iterations) to ~7e-6 (128) of the samples mismatched; a wider band
+        // (ctc_ctx_set_fast_band) trades speed for fewer of them: profiles/sign_probe_r2.md.
+        const float kappa = ctx ? ctx->kappa : kDefaultKappa;
         d.kappa = kappa;
     } else if (s->kind == CTC_SHAPE_SPHERE) {
         d.cx = s->center[0]; d.cy = s->center[1]; d.cz = s->center[2]; d.radius = s->radius;
@@ -266,7 +276,9 @@ void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint3
     // R >= 32: the R^3 core and the x = R / y = R faces go to the warp-walk path; a warp walks
     // L = 64 z-samples of its 8 columns when R >= 64 (else 32): per-warp set-up paid once per 512 samples
     const size_t R2 = (size_t)R * R, R3 = R2 * R;
-    const uint32_t lgw = lg >= 6 ? 1u : 0u;
+    // (small batches -- the drop-in's steady state is 8 leaves per split -- walk 32: twice the warps, half the
+    // dependent chain, the SMs are far from full anyway)
+    const uint32_t lgw = (lg >= 6 && (size_t)nspans * R3 >= ((size_t)1 << 23)) ? 1u : 0u;
     const size_t warp_blocks = lg >= 5 ? (R3 + 2 * R2) / (256u << lgw) : 0;
     const uint32_t core_blocks = (uint32_t)((warp_blocks + 7) / 8);
     const size_t rest = core_blocks ? R2 + 3 * (size_t)R + 1 : n3;
@@ -317,8 +329,9 @@ int sample_grids_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* span
     if (nspans == 0) return CTC_OK;
     if (!d_grids) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "grids is NULL");
     CK(cudaSetDevice(ctx->device));
-    // the pinned geometry staging buffer may still be in flight from a previous call
-    CK(cudaStreamSynchronize(ctx->stream));
+    // the pinned geometry staging buffer may still be in flight from a previous ASYNCHRONOUS call (the
+    // host-pointer entry points return synchronised)
+    if (ctx->async_inflight) { CK(cudaStreamSynchronize(ctx->stream)); ctx->async_inflight = false; }
     rc = upload_geom(ctx, spans, nspans, R); if (rc) return rc;
     const size_t n3 = (size_t)(R + 1) * (R + 1) * (R + 1);
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
@@ -394,7 +407,8 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     if ((reinterpret_cast<uintptr_t>(d_idx) & 7u) || (reinterpret_cast<uintptr_t>(d_v) & 3u))
         return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "output buffers must be 8-byte (indices) / 4-byte (vertices) aligned");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));   // staging buffers / events of a previous call
+    // staging buffers / events of a previous ASYNCHRONOUS call (host-pointer calls return synchronised)
+    if (ctx->async_inflight) { CK(cudaStreamSynchronize(ctx->stream)); ctx->async_inflight = false; }
     ctx->ev_used = 0; ctx->ev_pairs.clear();
     ctx->mesh_pending = true;
     ctx->n_groups = 0;
@@ -582,6 +596,7 @@ int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ct
         CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->async_inflight = false;
     const MeshState* st = static_cast<const MeshState*>(ctx->h_state.p);
     if (n_vertices) *n_vertices = st->total_v;
     if (n_indices) *n_indices = 6ull * st->total_q;
@@ -654,7 +669,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
                       &c->chunk_pre, &c->word_vpre, &c->word_qpre, &c->cell_of, &c->state, &c->out_v, &c->out_idx,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
-    c->h_geom.release(); c->h_state.release(); c->h_tables.release();
+    c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->k1_done) cudaEventDestroy(e);
@@ -730,6 +745,7 @@ int ctc_ctx_synchronize(ctc_ctx* ctx) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->async_inflight = false;
     return CTC_OK;
 }
 
@@ -774,7 +790,9 @@ int ctc_sample_grids_device(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span
                             uint32_t resolution, float* d_grids) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return sample_grids_impl(ctx, shape, spans, nspans, resolution, d_grids);
+    const int rc = sample_grids_impl(ctx, shape, spans, nspans, resolution, d_grids);
+    ctx->async_inflight = true;
+    return rc;
 }
 
 int ctc_sample_grids(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
@@ -807,6 +825,7 @@ int ctc_mesh_spans_device(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* 
                           uint64_t* d_i_off) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->async_inflight = true;
     return guarded(ctx, [&] { return mesh_spans_impl(ctx, shape, spans, nspans, resolution, d_v, vcap, d_idx, icap, d_v_off, d_i_off); });
 }
 
@@ -884,12 +903,150 @@ static int mesh_spans_host(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span*
     return status;
 }
 
+}  // extern "C" (reopened below)
+
+// A queued host-pointer mesh call (see ctc_ctx::q).
+struct MeshRequest {
+    const ctc_shape* shape; const ctc_span* spans; size_t nspans; uint32_t resolution;
+    ctc_vertex* v; size_t vcap; uint32_t* idx; size_t icap; uint64_t* v_off; uint64_t* i_off; ctc_timings* timings;
+    int status = CTC_OK;
+    std::string err;
+    bool done = false;
+};
+
+namespace {
+
+bool same_shape(const ctc_shape& a, const ctc_shape& b) {
+    return a.kind == b.kind && a.power == b.power && a.max_iters == b.max_iters && a.flags == b.flags &&
+           memcmp(&a.bailout, &b.bailout, sizeof(float)) == 0 && memcmp(a.center, b.center, sizeof a.center) == 0 &&
+           memcmp(&a.radius, &b.radius, sizeof(float)) == 0;
+}
+
+int run_request(ctc_ctx* ctx, MeshRequest* r) {
+    return guarded(ctx, [&] {
+        return mesh_spans_host(ctx, r->shape, r->spans, r->nspans, r->resolution, r->v, r->vcap, r->idx, r->icap, r->v_off,
+                               r->i_off, r->timings);
+    });
+}
+
+// One batched launch for several queued requests of the same shape and resolution: the spans are
+// concatenated, the batch is meshed into the context's pinned staging buffers, and every request gets its
+// slice (offset tables rebased to its own buffers).  Anything but a clean batch -- an error status, or a
+// request whose buffers are too small -- falls back to running the requests one by one, which reproduces
+// the per-call error contract exactly.
+void run_batch(ctc_ctx* ctx, std::vector<MeshRequest*>& batch) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto one_by_one = [&] {
+        for (MeshRequest* r : batch) { r->status = run_request(ctx, r); r->err = ctx->err; }
+    };
+    if (batch.size() == 1) { one_by_one(); return; }
+    size_t nspans = 0, vcap = 0, icap = 0;
+    for (MeshRequest* r : batch) { nspans += r->nspans; vcap += r->vcap; icap += r->icap; }
+    const int rc = guarded(ctx, [&]() -> int {
+        ctx->b_spans.clear();
+        for (MeshRequest* r : batch) ctx->b_spans.insert(ctx->b_spans.end(), r->spans, r->spans + r->nspans);
+        ctx->b_voff.assign(nspans + 1, 0); ctx->b_ioff.assign(nspans + 1, 0);
+        CK(cudaSetDevice(ctx->device));
+        CK(ctx->b_v.ensure((vcap ? vcap : 1) * sizeof(ctc_vertex)));
+        CK(ctx->b_i.ensure((icap ? icap : 1) * sizeof(uint32_t)));
+        ctc_timings t{};
+        const int st = mesh_spans_host(ctx, batch[0]->shape, ctx->b_spans.data(), nspans, batch[0]->resolution,
+                                       static_cast<ctc_vertex*>(ctx->b_v.p), vcap, static_cast<uint32_t*>(ctx->b_i.p), icap,
+                                       ctx->b_voff.data(), ctx->b_ioff.data(), &t);
+        if (st != CTC_OK) return st;
+        size_t s0 = 0;
+        for (MeshRequest* r : batch) {      // does every request's slice fit its own buffers?
+            const uint64_t nv = ctx->b_voff[s0 + r->nspans] - ctx->b_voff[s0], ni = ctx->b_ioff[s0 + r->nspans] - ctx->b_ioff[s0];
+            if (nv > r->vcap || ni > r->icap) return CTC_ERR_OVERFLOW;
+            s0 += r->nspans;
+        }
+        s0 = 0;
+        const double share = 1.0 / (double)(nspans ? nspans : 1);
+        for (MeshRequest* r : batch) {
+            const uint64_t v0 = ctx->b_voff[s0], i0 = ctx->b_ioff[s0];
+            const uint64_t nv = ctx->b_voff[s0 + r->nspans] - v0, ni = ctx->b_ioff[s0 + r->nspans] - i0;
+            if (nv) memcpy(r->v, static_cast<ctc_vertex*>(ctx->b_v.p) + v0, nv * sizeof(ctc_vertex));
+            if (ni) memcpy(r->idx, static_cast<uint32_t*>(ctx->b_i.p) + i0, ni * sizeof(uint32_t));
+            for (size_t k = 0; k <= r->nspans; ++k) { r->v_off[k] = ctx->b_voff[s0 + k] - v0; r->i_off[k] = ctx->b_ioff[s0 + k] - i0; }
+            if (r->timings) {   // the batch's kernels served every request: device time is apportioned by span count
+                const double f = share * (double)r->nspans;
+                r->timings->first_ms = t.first_ms * f; r->timings->second_ms = t.second_ms * f; r->timings->third_ms = t.third_ms * f;
+                r->timings->vertices = nv; r->timings->faces = ni / 6;
+            }
+            r->status = CTC_OK;
+            s0 += r->nspans;
+        }
+        ctx->batches++; ctx->batched_requests += batch.size();
+        return CTC_OK;
+    });
+    if (rc != CTC_OK) one_by_one();
+}
+
+}  // namespace
+
+extern "C" {
+
 int ctc_mesh_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
                    ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
                    ctc_timings* timings) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    MeshRequest req{shape, spans, nspans, resolution, v, vcap, idx, icap, v_off, i_off, timings};
+    // Destinations the device copies to directly (peer / device memory) and large calls gain nothing from
+    // coalescing: they go straight through.
+    bool direct = !ctx->coalesce || !shape || !v_off || !i_off || nspans == 0 || nspans > 64;
+    if (!direct) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, v ? static_cast<const void*>(v) : static_cast<const void*>(v_off)) == cudaSuccess &&
+            (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged))
+            direct = true;
+        (void)cudaGetLastError();
+    }
+    if (direct) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        return run_request(ctx, &req);
+    }
+    std::unique_lock<std::mutex> ql(ctx->q_mu);
+    ctx->q.push_back(&req);
+    if (ctx->q_leader) {                      // somebody is launching: wait for a leader to serve this request
+        ctx->q_cv.wait(ql, [&] { return req.done; });
+        if (req.status != CTC_OK) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = req.err; }
+        return req.status;
+    }
+    ctx->q_leader = true;                     // lead: serve the queue until it is empty (own request included)
+    while (!ctx->q.empty()) {
+        std::vector<MeshRequest*> batch;
+        size_t total = 0;
+        for (size_t k = 0; k < ctx->q.size();) {          // everything compatible with the queue's head, up to 4096 spans
+            MeshRequest* r = ctx->q[k];
+            if (batch.empty() || (r->resolution == batch[0]->resolution && same_shape(*r->shape, *batch[0]->shape) && total + r->nspans <= 4096)) {
+                batch.push_back(r); total += r->nspans;
+                ctx->q.erase(ctx->q.begin() + (long)k);
+            } else ++k;
+        }
+        ql.unlock();
+        run_batch(ctx, batch);
+        ql.lock();
+        for (MeshRequest* r : batch) r->done = true;
+        ctx->q_cv.notify_all();
+    }
+    ctx->q_leader = false;
+    if (req.status != CTC_OK) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = req.err; }
+    return req.status;
+}
+
+int ctc_ctx_set_coalescing(ctc_ctx* ctx, int enable) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->q_mu);
+    ctx->coalesce = enable != 0;
+    return CTC_OK;
+}
+
+int ctc_ctx_coalescing_stats(ctc_ctx* ctx, uint64_t* batches, uint64_t* requests) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    return guarded(ctx, [&] { return mesh_spans_host(ctx, shape, spans, nspans, resolution, v, vcap, idx, icap, v_off, i_off, timings); });
+    if (batches) *batches = ctx->batches;
+    if (requests) *requests = ctx->batched_requests;
+    return CTC_OK;
 }
 
 int ctc_ray_march(ctc_ctx* ctx, const ctc_shape* shape, const float* origin, const float* dir, size_t n,
@@ -1047,7 +1204,6 @@ int ctc_ctx_set_fast_band(ctc_ctx* ctx, float kappa) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!(kappa >= 0.0f)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "kappa must be >= 0");
     ctx->kappa = kappa > 0.0f ? kappa : kDefaultKappa;
-    ctx->kappa_user = kappa > 0.0f;
     return CTC_OK;
 }
 

@@ -676,9 +676,11 @@ template <bool kFast, int kVariant, bool kBand = true>
 __device__ __forceinline__ float shape_de(const ShapeDev& s, float px, float py, float pz) {
     if (kVariant == kVarSphere) return sphere_de(s, px, py, pz);
     if (kFast) {
+        // (generic powers: exact mode itself is a tolerance path there -- CUDA's libm against glibc's -- so the
+        // sign band would buy nothing; only the z-axis / NaN rule sends a sample to the exact evaluation)
         bool suspect;
         float d = (kVariant == kVarP8) ? mandelbulb_de_fast_p8<kBand>(s, px, py, pz, suspect)
-                                       : mandelbulb_de_fast_generic<kBand>(s, px, py, pz, suspect);
+                                       : mandelbulb_de_fast_generic<false>(s, px, py, pz, suspect);
         if (suspect) d = mandelbulb_de_exact_cold<kVariant == kVarP8>(s, px, py, pz);
         return d;
     }

@@ -15,9 +15,11 @@
  * fallback: without a CUDA device every call fails with CTC_ERR_CUDA /
  * CTC_ERR_NO_DEVICE.
  *
- * Threading: a ctc_ctx may be used from any thread (Shape: Sync + Send);
- * calls on one context are serialised by an internal mutex.  Create one
- * context per worker thread for concurrent submission.
+ * Threading: a ctc_ctx may be used from any thread (Shape: Sync + Send).
+ * Concurrent ctc_mesh_spans calls on ONE context (the reference meshes one
+ * leaf per thread-pool job, src/mesh/mod.rs:141-148) are coalesced by an
+ * internal submission queue into batched launches; every other entry point
+ * serialises on the context's mutex.
  */
 #ifndef CANTUCCI_B200_H
 #define CANTUCCI_B200_H
@@ -166,6 +168,14 @@ CTC_API int ctc_mesh_spans(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span 
                    uint32_t resolution,
                    ctc_vertex *v, size_t vcap, uint32_t *idx, size_t icap,
                    uint64_t *v_off, uint64_t *i_off, ctc_timings *timings);
+
+/* Concurrent small ctc_mesh_spans calls (<= 64 spans, host destinations) of one context are coalesced:
+ * the caller that finds the context idle launches; calls that arrive meanwhile queue up and are served
+ * by ONE batched launch per shape/resolution (results and per-call error statuses are exactly those of
+ * separate calls; pass timings of a batch are apportioned by span count).  0 disables it.
+ * ctc_ctx_coalescing_stats: batched launches so far and the requests they served. */
+CTC_API int ctc_ctx_set_coalescing(ctc_ctx *ctx, int enable);
+CTC_API int ctc_ctx_coalescing_stats(ctc_ctx *ctx, uint64_t *batches, uint64_t *requests);
 
 /* Device-resident variant: d_v / d_idx / d_v_off / d_i_off are device
  * pointers, `spans` stays a host pointer.  Asynchronous on the context's

@@ -33,3 +33,73 @@ def test_concurrent_callers_get_identical_meshes(ctx):
         for a, b in zip(out, want):
             assert np.array_equal(a.indices, b.indices)
             assert np.array_equal(a.vertices.view(np.uint32), b.vertices.view(np.uint32))
+
+
+def test_concurrent_single_span_calls_are_coalesced(ctx):
+    """SURVEY 8b threading bullet: the reference calls generate_for_box from num_cpus worker threads at once
+    (mesh/mod.rs:141-148).  On ONE context those calls are coalesced into batched launches: results stay
+    those of separate calls, and 16 concurrent single-span calls cost about as much as ONE 16-span call
+    plus one single-span call -- not 16 of them."""
+    import ctypes as C
+    import time
+    import cantucci_b200 as cb
+    from cantucci_b200 import _lib
+    L = _lib.lib()
+    spans = startup_leaves()[16:32]
+    sh = cb.Mandelbulb.classic(6, 2.5, fast=True)._ctc_shape()
+    n = len(spans)
+    bufs = [(np.empty(40_000, dtype=cb.VERTEX_DTYPE), np.empty(240_000, dtype=np.uint32), np.zeros(2, np.uint64), np.zeros(2, np.uint64))
+            for _ in range(n)]
+
+    def single(k):
+        v, i, vo, io = bufs[k]
+        rc = L.ctc_mesh_spans(ctx.handle, C.byref(sh), spans[k:k + 1].ctypes.data, 1, 64, v.ctypes.data, len(v), i.ctypes.data, len(i),
+                              vo.ctypes.data, io.ctypes.data, None)
+        assert rc == 0, ctx.last_error()
+
+    def batched():
+        v = np.empty(640_000, dtype=cb.VERTEX_DTYPE); i = np.empty(3_840_000, dtype=np.uint32)
+        vo = np.zeros(n + 1, np.uint64); io = np.zeros(n + 1, np.uint64)
+        rc = L.ctc_mesh_spans(ctx.handle, C.byref(sh), spans.ctypes.data, n, 64, v.ctypes.data, len(v), i.ctypes.data, len(i),
+                              vo.ctypes.data, io.ctypes.data, None)
+        assert rc == 0
+        return v, i, vo, io
+
+    def concurrent():
+        th = [threading.Thread(target=single, args=(k,)) for k in range(n)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    ref = batched()
+    concurrent()                                           # warm-up (staging buffers)
+    b0, r0 = ctx.coalescing_stats()
+    t_conc = min(concurrent() for _ in range(5))
+    b1, r1 = ctx.coalescing_stats()
+    assert b1 > b0 and (r1 - r0) > (b1 - b0)              # batched launches served several requests each
+    for k in range(n):                                     # every caller got exactly its span's mesh
+        v, i, vo, io = bufs[k]
+        a, b = int(ref[2][k]), int(ref[2][k + 1]); c, d = int(ref[3][k]), int(ref[3][k + 1])
+        assert int(vo[1]) == b - a and int(io[1]) == d - c
+        assert np.array_equal(v[: b - a].view(np.uint32), ref[0][a:b].view(np.uint32))
+        assert np.array_equal(i[: d - c], ref[1][c:d])
+    t0 = time.perf_counter(); batched(); t_batched = time.perf_counter() - t0
+    t0 = time.perf_counter(); single(0); t_single = time.perf_counter() - t0
+    # serialised, the 16 calls would cost 16 x t_single; coalesced they cost about one single call + one batch
+    # (thread start-up included, hence the slack)
+    assert t_conc < 3.0 * (t_batched + t_single) + 2e-3, (t_conc, t_batched, t_single)
+    # per-call error contract survives the batching: a caller with too-small buffers gets ITS overflow
+    tiny = (np.empty(4, dtype=cb.VERTEX_DTYPE), np.empty(24, dtype=np.uint32), np.zeros(2, np.uint64), np.zeros(2, np.uint64))
+    bufs[3] = tiny
+    rcs = [None] * n
+
+    def single_rc(k):
+        v, i, vo, io = bufs[k]
+        rcs[k] = L.ctc_mesh_spans(ctx.handle, C.byref(sh), spans[k:k + 1].ctypes.data, 1, 64, v.ctypes.data, len(v), i.ctypes.data, len(i),
+                                  vo.ctypes.data, io.ctypes.data, None)
+    th = [threading.Thread(target=single_rc, args=(k,)) for k in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert rcs[3] == _lib.CTC_ERR_OVERFLOW and int(tiny[2][1]) == int(ref[2][4] - ref[2][3])
+    assert all(rc == 0 for k, rc in enumerate(rcs) if k != 3)
