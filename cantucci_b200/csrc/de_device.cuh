@@ -366,17 +366,17 @@ __device__ __forceinline__ void p8_elevation(V z, V z2, V w, V w2, V& A, V& Zhn)
     Zhn = L::mul(c4, q4n);                                  // -Im (z + i w)^8 / 2
 }
 
-// dr = 8 r^7 dr + 1 from r^2; r^7 is kept for the polar-stretch bookkeeping
+// dr = 8 r^7 dr + 1 from r^2; g = 8 r^7 (the step's radial stretch) is kept for the error bookkeeping
 template <class V>
-__device__ __forceinline__ V p8_dr(V r2, V dr, V& r7) {
+__device__ __forceinline__ V p8_dr(V r2, V dr, V& g) {
     using L = Lanes<V>;
     const V r4 = L::mul(r2, r2);
-    r7 = L::mul(L::mul(r4, r2), L::sqrt(r2));
-    return L::fma(L::mul(r7, L::bc(8.0f)), dr, L::bc(1.0f));
+    g = L::mul(L::mul(L::mul(r4, r2), L::sqrt(r2)), L::bc(8.0f));
+    return L::fma(g, dr, L::bc(1.0f));
 }
 
 // z <- z^8 + p (the rotate and the "+ p" of mandelbulb.rs:74 in one FMA each).  A = Re (z + i w)^8
-// (the new distance from the z axis before "+ p") and iw = 1 / w go to the polar-stretch bookkeeping.
+// (the new distance from the z axis before "+ p") and iw = 1 / w go to the error bookkeeping.
 template <class V>
 __device__ __forceinline__ void p8_step(V& zx, V& zy, V& zz, V z2, V w2, V px, V py, V pz, V& A, V& iw) {
     using L = Lanes<V>;
@@ -388,23 +388,6 @@ __device__ __forceinline__ void p8_step(V& zx, V& zy, V& zz, V z2, V w2, V px, V
     zy = L::fma(L::mul(A, L::bc(-2.0f)), s8hn, py);
     zz = L::fma(L::bc(-2.0f), Zhn, pz);
 }
-
-// Extra error amplification of one step near the poles.  The triplex power is not conformal: a
-// perturbation along the azimuth is stretched by 8 |A| / w (A = Re (z + i w)^8, the new distance from
-// the z axis) where the radial and polar directions see 8 r^7 -- up to 8 r / w more, and dr (= the
-// reference's own derivative estimate) only carries 8 r^7.  Kept in the log domain on raw float bits
-// (2^23 per octave, piecewise-linear lg): max(0, lg |A| + lg 1/w - lg r^7) -- four ALU-pipe
-// instructions per sample and iteration, none on the FMA pipe that bounds the kernel.
-__device__ __forceinline__ int polar_stretch_log(float A, float iw, float r7) {
-    const int t = (int)(__float_as_uint(A) & 0x7fffffffu) + (int)__float_as_uint(iw) - (int)__float_as_uint(r7);
-    return max(t - 0x3f800000, 0);
-}
-// An iterate within ~1e-3 r of the z axis stretches by >= 2^10 in that one step: the accumulated
-// stretch doubles as the "touched the z axis" test (the reference's w^8 underflows there, its arithmetic
-// turns inf/NaN, and the fast path's 1/w is inf on the axis itself).
-constexpr int kAxisLog = 10 << 23;
-// accumulated stretch as a float factor (same piecewise-linear exponential; clamped far below overflow)
-__device__ __forceinline__ float polar_factor(int logp) { return __int_as_float(0x3f800000 + min(logp, 0x20000000)); }
 
 // 0.5 * ln(r) * r / dr with ln(r) = 0.5 * ln2 * lg2(r2)
 __device__ __forceinline__ float de_fast_epilogue(float r2, float dr) {
@@ -418,89 +401,88 @@ __device__ __forceinline__ float de_fast_epilogue(float r2, float dr) {
 // 0.5 ln(r) r / dr is decided by ONE comparison: a sample that leaves through `r > bailout` is
 // positive; one that runs all max_iters iterations is negative iff its last radius is < 1.  (A
 // borderline bailout decision cannot flip the sign: with r ~ bailout the next radius is ~ bailout^8.)
-// The fast path's r^2 differs from the reference's by at most ~ kappa * dr: dr obeys the same
-// recurrence as a first-order bound on the orbit's accumulated rounding error
-// (e' = 8 r^7 e + eta  vs  dr' = 8 r^7 dr + 1).  A sample is SUSPECT, and re-evaluated with the
-// exact-order IEEE arithmetic, when
-//   * it did not escape and |r^2 - 1| <= kappa * max_k dr_k * S  (sign of ln r not certain), or
-//   * it escaped but kappa * max_k dr_k * S is O(1)              (the orbit itself is not certain), or
-//   * S >= 2^10: some iterate came within ~1e-3 r of the z axis  (the reference's w^8 underflows there and
-//                                                                 its arithmetic turns inf/NaN), or
+// So the question is how far the fast path's last r^2 can be from the reference's.  To first order the
+// orbit's accumulated rounding error obeys  e' = L e + eta  with L the largest stretch of the step:
+//   * 8 r^7 radially and along the polar angle (what the reference's own dr carries), but
+//   * 8 |A| / w along the azimuth (A = Re (z + i w)^8, the new distance from the z axis): the triplex
+//     power is not conformal, near the poles it stretches azimuthal perturbations up to 8 r / w more.
+//     Without this term four of the 1.1 G samples of the benched volume sit outside any useful band.
+// The bound is kept in the LOG domain on raw float bits (2^23 per octave, piecewise-linear lg):
+//     le' = max(le + max(lg 8 r^7, lg 8 |A| / w), 0),     Amp.lemax = max_k le_k
+// -- seven ALU-pipe instructions per sample and iteration, none on the FMA pipe that bounds the kernels.
+// Unlike a product of per-step factors it CONTRACTS where the map contracts, so a long orbit that
+// settles on an attracting cycle stays trustworthy while a chaotic one does not.
+// A sample is SUSPECT, and re-evaluated with the exact-order IEEE arithmetic, when
+//   * it did not escape and |r^2 - 1| <= kappa 2^lemax           (sign of ln r not certain), or
+//   * it escaped but kappa 2^lemax is O(1)                        (the orbit itself is not certain), or
+//   * some iterate came within 2^-13 of the z axis               (the reference's w^8 underflows there, its
+//                                                                 arithmetic turns inf/NaN, and the fast path's
+//                                                                 1/w is inf on the axis itself), or
 //   * anything is NaN (all tests are written so that NaN is suspect).
-// S is the accumulated polar stretch (polar_stretch_log): near the poles the map stretches azimuthal
-// perturbations up to 8 r / w more than the 8 r^7 that dr carries; without S four of the 1.1 G samples
-// of the benched volume escape the band at any useful kappa, with it none does (profiles/sign_probe_r2.md).
 // kappa is calibrated on the GPU (ctc_fast_sign_probe, profiles/sign_probe_r2.md).
-// kBand = false keeps only the axis/NaN rules (E3: values, not signs).
+// kBand = false keeps only the axis/NaN rules (E3 and the generic powers: values, not signs).
 // ---------------------------------------------------------------------------
+constexpr int kFloatBias = 0x3f800000;
+constexpr int kAxisIwBits = 0x46000000;       // bits of 8192.0f: 1/w >= 2^13
+
+struct Amp { int le, lemax, iwmax; };
+
+__device__ __forceinline__ Amp amp_init() { return Amp{0, 0, 0}; }
+
+// one step: g = 8 r^7 (float), A, iw as above
 template <bool kBand>
-__device__ __forceinline__ bool fast_suspect_escaped(const ShapeDev& s, float drmax, int logp) {
-    return logp >= kAxisLog || (kBand && !(s.kappa * drmax * polar_factor(logp) < 4.0f));
-}
-template <bool kBand>
-__device__ __forceinline__ bool fast_suspect_inside(const ShapeDev& s, float r2, float drmax, int logp) {
-    if (!kBand) return logp >= kAxisLog || !(r2 == r2);
-    return logp >= kAxisLog || !(fabsf(r2 - 1.0f) > s.kappa * drmax * polar_factor(logp));
+__device__ __forceinline__ void amp_step(Amp& a, float g, float A, float iw) {
+    const unsigned iwb = __float_as_uint(iw);
+    a.iwmax = max(a.iwmax, (int)iwb);
+    if (kBand) {
+        // lg(8 |A| / w) + bias = bits|A| + bits(1/w) + 3 octaves - bias        (u32: cannot overflow for finite A)
+        const unsigned xa = (__float_as_uint(A) & 0x7fffffffu) + iwb - (unsigned)(kFloatBias - (3 << 23));
+        const unsigned x = max(xa, __float_as_uint(g));
+        a.le = max((int)((unsigned)a.le + x - (unsigned)kFloatBias), 0);
+        a.lemax = max(a.lemax, a.le);
+    }
 }
 
-// FAST power-8 DE of one sample.
-struct FastInfo { float r2, dr, drmax, wmin; uint32_t escaped; float polar; float wrmin; };   // probe output (ctc_fast_sign_probe)
+// 2^lemax as a float factor (same piecewise-linear exponential; clamped far below overflow)
+__device__ __forceinline__ float amp_factor(const Amp& a) { return __int_as_float(kFloatBias + min(a.lemax, 0x20000000)); }
+
+template <bool kBand>
+__device__ __forceinline__ bool fast_suspect_escaped(const ShapeDev& s, const Amp& a) {
+    return a.iwmax >= kAxisIwBits || (kBand && !(s.kappa * amp_factor(a) < 4.0f));
+}
+template <bool kBand>
+__device__ __forceinline__ bool fast_suspect_inside(const ShapeDev& s, float r2, const Amp& a) {
+    if (!kBand) return a.iwmax >= kAxisIwBits || !(r2 == r2);
+    return a.iwmax >= kAxisIwBits || !(fabsf(r2 - 1.0f) > s.kappa * amp_factor(a));
+}
+
+struct FastInfo { float r2, dr, amp; uint32_t escaped, axis; };   // probe output (ctc_fast_sign_probe)
 
 // FAST power-8 DE of one sample.
 template <bool kBand>
-__device__ __forceinline__ float mandelbulb_de_fast_p8(const ShapeDev& s, float px, float py, float pz, bool& suspect) {
+__device__ __forceinline__ float mandelbulb_de_fast_p8(const ShapeDev& s, float px, float py, float pz, bool& suspect,
+                                                       FastInfo* info = nullptr) {
     using L = Lanes<float>;
-    float zx = px, zy = py, zz = pz, dr = 1.0f, drmax = 1.0f, r2;
-    int logp = 0;
+    float zx = px, zy = py, zz = pz, dr = 1.0f, r2;
+    Amp amp = amp_init();
     uint32_t left = s.max_iters;                 // >= 1 (checked on the host, mandelbulb.rs:20)
     for (;;) {
         const float z2 = L::mul(zz, zz);
         const float w2 = L::fma(zx, zx, L::mul(zy, zy));
         r2 = L::add(w2, z2);
         if (r2 > s.bail2) {                      // r > bailout, on squares
-            suspect = fast_suspect_escaped<kBand>(s, drmax, logp);
+            suspect = fast_suspect_escaped<kBand>(s, amp);
+            if (info) *info = FastInfo{r2, dr, amp_factor(amp), 1u, amp.iwmax >= kAxisIwBits ? 1u : 0u};
             return de_fast_epilogue(r2, dr);
         }
-        float r7, A, iw;
-        dr = p8_dr<float>(r2, dr, r7);
-        drmax = fmaxf(drmax, dr);
+        float g, A, iw;
+        dr = p8_dr<float>(r2, dr, g);
         if (--left == 0u) break;                 // the reference's last rotate is dead work
         p8_step<float>(zx, zy, zz, z2, w2, px, py, pz, A, iw);
-        logp += polar_stretch_log(A, iw, r7);
+        amp_step<kBand>(amp, g, A, iw);
     }
-    suspect = fast_suspect_inside<kBand>(s, r2, drmax, logp);
-    return de_fast_epilogue(r2, dr);
-}
-
-// The same evaluation, instrumented for ctc_fast_sign_probe (identical operations, identical bits).
-__device__ __forceinline__ float mandelbulb_de_fast_p8_probe(const ShapeDev& s, float px, float py, float pz, FastInfo& info) {
-    using L = Lanes<float>;
-    float zx = px, zy = py, zz = pz, dr = 1.0f, drmax = 1.0f, r2;
-    float wmin = __int_as_float(0x7f800000), wrmin = 1.0f;
-    int logp = 0;
-    uint32_t left = s.max_iters, escaped = 0u;
-    for (;;) {
-        const float z2 = L::mul(zz, zz);
-        const float w2 = L::fma(zx, zx, L::mul(zy, zy));
-        r2 = L::add(w2, z2);
-        wmin = fminf(wmin, w2);
-        if (r2 > s.bail2) { escaped = 1u; break; }
-        wrmin = fminf(wrmin, w2 / r2);
-        const float r4 = L::mul(r2, r2);
-        const float r7 = L::mul(L::mul(r4, r2), L::sqrt(r2));
-        dr = L::fma(L::mul(r7, 8.0f), dr, 1.0f);
-        drmax = fmaxf(drmax, dr);
-        if (--left == 0u) break;
-        const float iw = L::rsqrt(w2);
-        float c8, s8hn, A, Zhn;
-        p8_azimuth<float>(zx, zy, iw, c8, s8hn);
-        p8_elevation<float>(zz, z2, L::mul(w2, iw), w2, A, Zhn);
-        logp += polar_stretch_log(A, iw, r7);
-        zx = L::fma(A, c8, px);
-        zy = L::fma(L::mul(A, -2.0f), s8hn, py);
-        zz = L::fma(-2.0f, Zhn, pz);
-    }
-    info = FastInfo{r2, dr, drmax, wmin, escaped, polar_factor(logp), wrmin};
+    suspect = fast_suspect_inside<kBand>(s, r2, amp);
+    if (info) *info = FastInfo{r2, dr, amp_factor(amp), 0u, amp.iwmax >= kAxisIwBits ? 1u : 0u};
     return de_fast_epilogue(r2, dr);
 }
 
@@ -511,17 +493,17 @@ __device__ __forceinline__ float mandelbulb_de_fast_p8_probe(const ShapeDev& s, 
 // share a lattice column.  (A variant that snapshots the escaping half and computes both distances in
 // packed form after the loop measured 10 % slower: the extra live registers cost more moves than the
 // duplicated epilogue costs instructions.)
-#define CTC_PAIR_ESCAPE_IMM(H, BIT)                                                              \
+#define CTC_PAIR_ESCAPE(H, BIT, AMP)                                                             \
     if (r2.H > bail2) {                                                                          \
         d.H = de_fast_epilogue(r2.H, dr.H);                                                      \
-        if (fast_suspect_escaped<kBand>(s, drmax.H, logp.H)) suspect |= BIT;                     \
+        if (fast_suspect_escaped<kBand>(s, AMP)) suspect |= BIT;                                 \
         done |= BIT;                                                                             \
         pz.H = __int_as_float(0x7fffffff);                                                       \
     }
 
 template <bool kBand>
 __device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float2 py, float2 pz, float2 zx, float2 zy, float2 zz,
-                                             float2 dr, float2 drmax, int2 logp, uint32_t left, float2& d,
+                                             float2 dr, Amp ampa, Amp ampb, uint32_t left, float2& d,
                                              uint32_t done, uint32_t& suspect) {
     using L = Lanes<float2>;
     const float bail2 = s.bail2;
@@ -532,25 +514,25 @@ __device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float
         const float2 w2 = L::fma(zx, zx, L::mul(zy, zy));
         r2 = L::add(w2, z2);
         if ((r2.x > bail2) | (r2.y > bail2)) {
-            CTC_PAIR_ESCAPE_IMM(x, 1u)
-            CTC_PAIR_ESCAPE_IMM(y, 2u)
+            CTC_PAIR_ESCAPE(x, 1u, ampa)
+            CTC_PAIR_ESCAPE(y, 2u, ampb)
             if (done == 3u) return;
         }
-        float2 r7, A, iw;
-        dr = p8_dr<float2>(r2, dr, r7);
-        drmax = L::vmax(drmax, dr);
+        float2 g, A, iw;
+        dr = p8_dr<float2>(r2, dr, g);
         if (--left == 0u) break;
         p8_step<float2>(zx, zy, zz, z2, w2, px, py, pz, A, iw);
-        logp.x += polar_stretch_log(A.x, iw.x, r7.x);
-        logp.y += polar_stretch_log(A.y, iw.y, r7.y);
+        amp_step<kBand>(ampa, g.x, A.x, iw.x);
+        amp_step<kBand>(ampb, g.y, A.y, iw.y);
     }
+    // the halves that ran all max_iters iterations
     if (!(done & 1u)) {
         d.x = de_fast_epilogue(r2.x, dr.x);
-        if (fast_suspect_inside<kBand>(s, r2.x, drmax.x, logp.x)) suspect |= 1u;
+        if (fast_suspect_inside<kBand>(s, r2.x, ampa)) suspect |= 1u;
     }
     if (!(done & 2u)) {
         d.y = de_fast_epilogue(r2.y, dr.y);
-        if (fast_suspect_inside<kBand>(s, r2.y, drmax.y, logp.y)) suspect |= 2u;
+        if (fast_suspect_inside<kBand>(s, r2.y, ampb)) suspect |= 2u;
     }
 }
 
@@ -559,8 +541,7 @@ template <bool kBand>
 __device__ __forceinline__ float2 mandelbulb_de_fast_p8_pair(const ShapeDev& s, float2 px, float2 py, float2 pz, uint32_t& suspect) {
     float2 d = make_float2(0.0f, 0.0f);
     suspect = 0u;
-    p8_pair_loop<kBand>(s, px, py, pz, px, py, pz, make_float2(1.0f, 1.0f), make_float2(1.0f, 1.0f),
-                        make_int2(0, 0), s.max_iters, d, 0u, suspect);
+    p8_pair_loop<kBand>(s, px, py, pz, px, py, pz, make_float2(1.0f, 1.0f), amp_init(), amp_init(), s.max_iters, d, 0u, suspect);
     return d;
 }
 
@@ -585,24 +566,23 @@ __device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeD
     using L = Lanes<float2>;
     const float bail2 = s.bail2;
     const float2 px = L::bc(px_), py = L::bc(py_);
-    float2 d = make_float2(0.0f, 0.0f), dr = L::bc(1.0f), drmax = L::bc(1.0f);
+    float2 d = make_float2(0.0f, 0.0f), dr = L::bc(1.0f);
     uint32_t done = 0u, left = s.max_iters;
-    int2 logp = make_int2(0, 0);
+    Amp ampa = amp_init(), ampb = amp_init();
     suspect = 0u;
     const float2 z2 = L::mul(pz, pz);
     const float2 w2 = L::bc(c.w2);
     float2 r2 = L::add(w2, z2);
     if ((r2.x > bail2) | (r2.y > bail2)) {
-        CTC_PAIR_ESCAPE_IMM(x, 1u)
-        CTC_PAIR_ESCAPE_IMM(y, 2u)
+        CTC_PAIR_ESCAPE(x, 1u, ampa)
+        CTC_PAIR_ESCAPE(y, 2u, ampb)
         if (done == 3u) return d;
     }
-    float2 r7;
-    dr = p8_dr<float2>(r2, dr, r7);
-    drmax = L::vmax(drmax, dr);
+    float2 g;
+    dr = p8_dr<float2>(r2, dr, g);
     if (--left == 0u) {
-        if (!(done & 1u)) { d.x = de_fast_epilogue(r2.x, dr.x); if (fast_suspect_inside<kBand>(s, r2.x, drmax.x, 0)) suspect |= 1u; }
-        if (!(done & 2u)) { d.y = de_fast_epilogue(r2.y, dr.y); if (fast_suspect_inside<kBand>(s, r2.y, drmax.y, 0)) suspect |= 2u; }
+        if (!(done & 1u)) { d.x = de_fast_epilogue(r2.x, dr.x); if (fast_suspect_inside<kBand>(s, r2.x, ampa)) suspect |= 1u; }
+        if (!(done & 2u)) { d.y = de_fast_epilogue(r2.y, dr.y); if (fast_suspect_inside<kBand>(s, r2.y, ampb)) suspect |= 2u; }
         return d;
     }
     float2 A, Zhn;
@@ -610,46 +590,46 @@ __device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeD
     const float2 zx = L::fma(A, L::bc(c.c8), px);
     const float2 zy = L::fma(L::mul(A, L::bc(-2.0f)), L::bc(c.s8hn), py);
     const float2 zz = L::fma(L::bc(-2.0f), Zhn, pz);
-    logp.x = polar_stretch_log(A.x, c.iw, r7.x);
-    logp.y = polar_stretch_log(A.y, c.iw, r7.y);
-    p8_pair_loop<kBand>(s, px, py, pz, zx, zy, zz, dr, drmax, logp, left, d, done, suspect);
+    amp_step<kBand>(ampa, g.x, A.x, c.iw);
+    amp_step<kBand>(ampb, g.y, A.y, c.iw);
+    p8_pair_loop<kBand>(s, px, py, pz, zx, zy, zz, dr, ampa, ampb, left, d, done, suspect);
     return d;
 }
-#undef CTC_PAIR_ESCAPE_IMM
+#undef CTC_PAIR_ESCAPE
 
 // FAST generic-power DE of one sample (config 4's P = 2, 4, 16, ...): trig-free complex binary powers
 //   (z + i w)^P = r^P (cos P.theta + i sin P.theta),   ((x + i y)/w)^P = cos P.phi + i sin P.phi
-template <bool kBand>
+// Exact mode itself is a tolerance path for these powers (CUDA's libm against glibc's), so no sign band
+// is kept: only the z-axis / NaN rule sends a sample to the exact evaluation.
 __device__ __forceinline__ float mandelbulb_de_fast_generic(const ShapeDev& s, float px, float py, float pz, bool& suspect) {
     const uint32_t P = s.power;
     const float bail2 = s.bail2;
     float zx = px, zy = py, zz = pz;
-    float dr = 1.0f, drmax = 1.0f, r2;
-    int logp = 0;
+    float dr = 1.0f, r2;
+    int iwmax = 0;
     uint32_t left = s.max_iters;
     for (;;) {
         const float z2 = zz * zz;
         const float w2 = fmaf(zx, zx, zy * zy);
         r2 = w2 + z2;
         if (r2 > bail2) {
-            suspect = fast_suspect_escaped<kBand>(s, drmax, logp);
+            suspect = iwmax >= kAxisIwBits;
             return de_fast_epilogue(r2, dr);
         }
         const float r = fast_sqrt(r2);
         float rp1 = 1.0f;                       // r^(P-1)
         { float cur = r; uint32_t n = P - 1u; while (n) { if (n & 1u) rp1 *= cur; n >>= 1; if (n) cur *= cur; } }
         dr = fmaf((float)P * rp1, dr, 1.0f);
-        drmax = fmaxf(drmax, dr);
         if (--left == 0u) break;
         const float iw = fast_rsqrt(w2);
+        iwmax = max(iwmax, __float_as_int(iw));
         const float w = w2 * iw;
         float ct, st, cp, sp;
         cpow(zz, w, P, ct, st);                 // r^P cos(P theta), r^P sin(P theta)
         cpow(zx * iw, zy * iw, P, cp, sp);      // cos(P phi), sin(P phi)
-        logp += polar_stretch_log(st, iw, rp1);      // azimuthal stretch P |r^P sin| / w against P r^(P-1)
         zx = fmaf(st, cp, px); zy = fmaf(st, sp, py); zz = ct + pz;
     }
-    suspect = fast_suspect_inside<kBand>(s, r2, drmax, logp);
+    suspect = iwmax >= kAxisIwBits || !(r2 == r2);
     return de_fast_epilogue(r2, dr);
 }
 
@@ -680,7 +660,7 @@ __device__ __forceinline__ float shape_de(const ShapeDev& s, float px, float py,
         // sign band would buy nothing; only the z-axis / NaN rule sends a sample to the exact evaluation)
         bool suspect;
         float d = (kVariant == kVarP8) ? mandelbulb_de_fast_p8<kBand>(s, px, py, pz, suspect)
-                                       : mandelbulb_de_fast_generic<false>(s, px, py, pz, suspect);
+                                       : mandelbulb_de_fast_generic(s, px, py, pz, suspect);
         if (suspect) d = mandelbulb_de_exact_cold<kVariant == kVarP8>(s, px, py, pz);
         return d;
     }

@@ -865,13 +865,14 @@ iteration_stats_points_kernel(ShapeDev sh, const float* __restrict__ xyz, size_t
 // Calibration of the sign-trust band (fast_suspect_*, de_device.cuh): every sample of the span batch is
 // evaluated by the fast path (raw, no repair) AND by the exact path.  out[] (unsigned long long):
 //   [0] samples                      [1] raw sign mismatches fast vs exact
-//   [2] mismatches with an iterate on the z axis (accumulated polar stretch >= 2^10)
+//   [2] mismatches with an iterate on the z axis (1/w >= 2^13)
 //   [3] samples not escaped in both  [4] samples whose escape status differs
-//   [5] max |r2_fast - r2_exact| / max dr over [3], as float bits    [6] the same over (max dr * polar stretch)
+//   [5] max |r2_fast - r2_exact| / dr over [3], as float bits    [6] the same over the amplification bound 2^lemax
 //   [7] mismatches where the fast path escaped
 //   [8 + 4q ..] for q = 0..23, kappa = 2^-(8+q), axis rule applied first:
-//        suspects / uncovered mismatches with the band kappa * max dr, then with kappa * max dr * polar stretch
-//   [kProbeWords ..] up to kProbeDump records of 12 floats: mismatches the band 2^-17 * max dr * stretch misses
+//        suspects / uncovered mismatches with the band kappa * dr (for reference), then with the production
+//        band kappa * 2^lemax (amp_step, de_device.cuh)
+//   [kProbeWords ..] up to kProbeDump records of 12 floats: mismatches the production band misses at kappa = 2^-17
 constexpr int kProbeKappas = 24;
 constexpr int kProbeWords = 8 + 4 * kProbeKappas;
 constexpr int kProbeDump = 64;
@@ -886,7 +887,7 @@ fast_sign_probe_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t 
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     const bool live = i < n3;
     bool mism = false, axis = false, esc_e = false, both_in = false;
-    FastInfo fi{1.0f, 1.0f, 1.0f, 1.0f, 1u, 1.0f, 1.0f};
+    FastInfo fi{1.0f, 1.0f, 1.0f, 1u, 0u};
     float e_max = 0.0f, e_pol = 0.0f, px = 0.f, py = 0.f, pz = 0.f, re = 0.f, df = 0.f, dx = 0.f;
     if (live) {
         uint32_t x, y, z;
@@ -895,16 +896,17 @@ fast_sign_probe_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t 
         px = __fadd_rn(g.s[0], __fmul_rn(g.across[0], __fmul_rn((float)x, inv_r)));
         py = __fadd_rn(g.s[1], __fmul_rn(g.across[1], __fmul_rn((float)y, inv_r)));
         pz = __fadd_rn(g.s[2], __fmul_rn(g.across[2], __fmul_rn((float)z, inv_r)));
-        df = mandelbulb_de_fast_p8_probe(sh, px, py, pz, fi);
+        bool susp_unused;
+        df = mandelbulb_de_fast_p8<true>(sh, px, py, pz, susp_unused, &fi);
         uint32_t it;
         dx = mandelbulb_de_exact<true>(sh, px, py, pz, &it, &re);
         esc_e = it < sh.max_iters;
         mism = (__float_as_uint(df) >> 31) != (__float_as_uint(dx) >> 31);
-        axis = !(fi.polar < 1024.0f);
+        axis = fi.axis != 0u;
         both_in = !fi.escaped && !esc_e;
         if (both_in && !axis) {
             const float err = fabsf(fi.r2 - re * re);
-            if (err == err) { e_max = err / fi.drmax; e_pol = err / (fi.drmax * fi.polar); }
+            if (err == err) { e_max = err / fi.dr; e_pol = err / fi.amp; }
         }
     }
     const uint32_t lane = threadIdx.x & 31u;
@@ -922,10 +924,10 @@ fast_sign_probe_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t 
     float kappa = 1.0f / 256.0f;
     for (int q = 0; q < kProbeKappas; ++q, kappa *= 0.5f) {
         bool s_max, s_pol;
-        if (fi.escaped) { s_max = axis || !(kappa * fi.drmax < 4.0f); s_pol = axis || !(kappa * fi.drmax * fi.polar < 4.0f); }
+        if (fi.escaped) { s_max = axis || !(kappa * fi.dr < 4.0f); s_pol = axis || !(kappa * fi.amp < 4.0f); }
         else {
-            s_max = axis || !(fabsf(fi.r2 - 1.0f) > kappa * fi.drmax);
-            s_pol = axis || !(fabsf(fi.r2 - 1.0f) > kappa * fi.drmax * fi.polar);
+            s_max = axis || !(fabsf(fi.r2 - 1.0f) > kappa * fi.dr);
+            s_pol = axis || !(fabsf(fi.r2 - 1.0f) > kappa * fi.amp);
         }
         CTC_PROBE_COUNT(8 + 4 * q, s_max)
         CTC_PROBE_COUNT(9 + 4 * q, mism && !s_max)
@@ -935,8 +937,8 @@ fast_sign_probe_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t 
             const unsigned int slot = atomicAdd(dump_count, 1u);
             if (slot < (unsigned)kProbeDump) {
                 float* o = dump + 12 * slot;
-                o[0] = px; o[1] = py; o[2] = pz; o[3] = fi.r2; o[4] = re * re; o[5] = fi.dr; o[6] = fi.drmax;
-                o[7] = fi.wmin; o[8] = fi.polar; o[9] = fi.wrmin; o[10] = df; o[11] = dx;
+                o[0] = px; o[1] = py; o[2] = pz; o[3] = fi.r2; o[4] = re * re; o[5] = fi.dr; o[6] = fi.amp;
+                o[7] = (float)fi.escaped; o[8] = esc_e ? 1.0f : 0.0f; o[9] = 0.0f; o[10] = df; o[11] = dx;
             }
         }
     }

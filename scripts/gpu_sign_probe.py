@@ -29,13 +29,13 @@ def probe(name, spans, iters, bail, R=64):
     f = lambda b: float(np.uint32(b).view(np.float32))
     rec = {"name": name, "spans": int(spans.shape[0]), "max_iters": iters, "bailout": bail, "samples": o[0],
            "raw_sign_mismatches": o[1], "mismatches_in_axis_band": o[2], "both_inside": o[3], "escape_status_differs": o[4],
-           "max_err_over_dr_max": f(o[5]), "max_err_over_dr_max_polar": f(o[6]), "mismatches_fast_escaped": o[7],
-           "uncovered_at_2^-17_polar": [[float(x) for x in r] for r in dump],
+           "max_err_over_dr": f(o[5]), "max_err_over_amp": f(o[6]), "mismatches_fast_escaped": o[7],
+           "uncovered_at_2^-17_amp": [[float(x) for x in r] for r in dump],
            "secs": round(time.time() - t0, 2), "kappa": []}
     for q in range(24):
         s_max, u_max, s_pol, u_pol = o[8 + 4 * q: 12 + 4 * q]
-        rec["kappa"].append({"log2": -(8 + q), "suspects_dr_max": s_max, "uncovered_dr_max": u_max,
-                             "suspects_polar": s_pol, "uncovered_polar": u_pol})
+        rec["kappa"].append({"log2": -(8 + q), "suspects_dr": s_max, "uncovered_dr": u_max,
+                             "suspects_amp": s_pol, "uncovered_amp": u_pol})
     print(json.dumps(rec), flush=True)
     return rec
 
