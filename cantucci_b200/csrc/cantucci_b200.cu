@@ -141,6 +141,22 @@ int guarded(ctc_ctx* ctx, F&& body) {
     }
 }
 
+// Smallest lemax for which the device's test "kappa * amp_factor(lemax) < 4" fails (amp_factor, de_device.cuh:
+// the float whose bits are bias + min(lemax, 2^29), monotone in lemax): escaped samples compare integers.
+int32_t amp_trust_threshold(float kappa) {
+    auto trusted = [kappa](int32_t le) {
+        const int32_t bits = 0x3f800000 + (le < 0x20000000 ? le : 0x20000000);
+        float f; memcpy(&f, &bits, 4);
+        volatile float prod = kappa * f;
+        return prod < 4.0f;
+    };
+    if (!trusted(0)) return 0;
+    if (trusted(0x20000000)) return 0x7fffffff;
+    int32_t lo = 0, hi = 0x20000000;            // trusted(lo), !trusted(hi)
+    while (hi - lo > 1) { const int32_t mid = lo + (hi - lo) / 2; if (trusted(mid)) lo = mid; else hi = mid; }
+    return hi;
+}
+
 // The reference's asserts on the shape (mandelbulb.rs:20) and what this build supports.
 int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
     if (!s) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "shape is NULL");
@@ -160,6 +176,7 @@ int check_shape(ctc_ctx* ctx, const ctc_shape* s, ShapeDev* out) {
         // (ctc_ctx_set_fast_band) trades speed for fewer of them: profiles/sign_probe_r2.md.
         const float kappa = ctx ? ctx->kappa : kDefaultKappa;
         d.kappa = kappa;
+        d.le_trust = amp_trust_threshold(kappa);
     } else if (s->kind == CTC_SHAPE_SPHERE) {
         d.cx = s->center[0]; d.cy = s->center[1]; d.cz = s->center[2]; d.radius = s->radius;
     } else {

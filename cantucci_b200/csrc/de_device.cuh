@@ -25,7 +25,9 @@ struct ShapeDev {
     uint32_t max_iters;  // clamped to 2^32-1 on the host
     float    bailout;
     float    bail2;      // bailout * bailout (host, IEEE): the FAST path tests squared radii
-    float    kappa;      // FAST: sign-trust band |r^2 - 1| <= kappa * max dr (see fast_suspect_*)
+    float    kappa;      // FAST: sign-trust band |r^2 - 1| <= kappa * 2^lemax (see fast_suspect_*)
+    int32_t  le_trust;   // FAST: smallest lemax with kappa * 2^lemax >= 4 (host, amp_trust_threshold): an escaped
+                         // sample's orbit is trusted below it -- one integer compare instead of a multiply
     float    cx, cy, cz, radius;
 };
 
@@ -394,6 +396,15 @@ __device__ __forceinline__ float de_fast_epilogue(float r2, float dr) {
     return (0.25f * 0.69314718056f) * fast_lg2(r2) * fast_sqrt(r2) * fast_rcp(dr);
 }
 
+// the same for both halves of a pair (same association, so the same bits as the scalar form)
+__device__ __forceinline__ float2 de_fast_epilogue2(float2 r2, float2 dr) {
+    const float2 lg = make_float2(fast_lg2(r2.x), fast_lg2(r2.y));
+    const float2 sq = make_float2(fast_sqrt(r2.x), fast_sqrt(r2.y));
+    const float2 rc = make_float2(fast_rcp(dr.x), fast_rcp(dr.y));
+    const float c = 0.25f * 0.69314718056f;
+    return __fmul2_rn(__fmul2_rn(__fmul2_rn(make_float2(c, c), lg), sq), rc);
+}
+
 // ---------------------------------------------------------------------------
 // Can the SIGN of a fast evaluation be trusted?  (DESIGN.md "sign-exact fast mode")
 //
@@ -446,9 +457,10 @@ __device__ __forceinline__ void amp_step(Amp& a, float g, float A, float iw) {
 // 2^lemax as a float factor (same piecewise-linear exponential; clamped far below overflow)
 __device__ __forceinline__ float amp_factor(const Amp& a) { return __int_as_float(kFloatBias + min(a.lemax, 0x20000000)); }
 
+// (kappa * amp_factor(lemax) is monotone in lemax, so "kappa 2^lemax >= 4" is lemax >= le_trust)
 template <bool kBand>
 __device__ __forceinline__ bool fast_suspect_escaped(const ShapeDev& s, const Amp& a) {
-    return a.iwmax >= kAxisIwBits || (kBand && !(s.kappa * amp_factor(a) < 4.0f));
+    return a.iwmax >= kAxisIwBits || (kBand && a.lemax >= s.le_trust);
 }
 template <bool kBand>
 __device__ __forceinline__ bool fast_suspect_inside(const ShapeDev& s, float r2, const Amp& a) {
@@ -488,17 +500,48 @@ __device__ __forceinline__ float mandelbulb_de_fast_p8(const ShapeDev& s, float 
 
 // Two samples per thread: the iteration loop shared by the column form (K1) and the point form (E3).
 // On entry (zx, zy, zz) hold the current iterate of both halves, `left` >= 1 radius tests remain.
-// A half that escapes gets its distance at once and is parked on NaN (its `+ p.z` operand), so it
-// neither escapes again nor disturbs the other half; (px, py) stay broadcast scalars when the halves
-// share a lattice column.  (A variant that snapshots the escaping half and computes both distances in
-// packed form after the loop measured 10 % slower: the extra live registers cost more moves than the
-// duplicated epilogue costs instructions.)
+// The common exits are packed: both halves leaving at the same radius test (neighbouring samples of a
+// lattice column almost always do) or both running all max_iters iterations take ONE epilogue in
+// FMUL2 form.  Otherwise a half that escapes alone gets its distance at once and is parked on NaN (its
+// `+ p.z` operand), so it neither escapes again nor disturbs the other half; (px, py) stay broadcast
+// scalars when the halves share a lattice column.  (A variant that snapshots the escaping half and
+// computes both distances in packed form after the loop measured 10 % slower: the extra live registers
+// cost more moves than the duplicated epilogue costs instructions.)
 #define CTC_PAIR_ESCAPE(H, BIT, AMP)                                                             \
     if (r2.H > bail2) {                                                                          \
         d.H = de_fast_epilogue(r2.H, dr.H);                                                      \
         if (fast_suspect_escaped<kBand>(s, AMP)) suspect |= BIT;                                 \
         done |= BIT;                                                                             \
         pz.H = __int_as_float(0x7fffffff);                                                       \
+    }
+// `return`s from the enclosing function when the pair is finished
+#define CTC_PAIR_RADIUS_TEST()                                                                   \
+    {                                                                                            \
+        const bool ex_ = r2.x > bail2, ey_ = r2.y > bail2;     /* a parked half is NaN: false */ \
+        if (ex_ | ey_) {                                                                         \
+            if (ex_ & ey_) {                                                                     \
+                d = de_fast_epilogue2(r2, dr);                                                   \
+                suspect |= (fast_suspect_escaped<kBand>(s, ampa) ? 1u : 0u) |                    \
+                           (fast_suspect_escaped<kBand>(s, ampb) ? 2u : 0u);                     \
+                return;                                                                          \
+            }                                                                                    \
+            CTC_PAIR_ESCAPE(x, 1u, ampa)                                                         \
+            CTC_PAIR_ESCAPE(y, 2u, ampb)                                                         \
+            if (done == 3u) return;                                                              \
+        }                                                                                        \
+    }
+// the halves that ran all max_iters iterations
+#define CTC_PAIR_TAIL()                                                                          \
+    if (done == 0u) {                                                                            \
+        d = de_fast_epilogue2(r2, dr);                                                           \
+        suspect |= (fast_suspect_inside<kBand>(s, r2.x, ampa) ? 1u : 0u) |                       \
+                   (fast_suspect_inside<kBand>(s, r2.y, ampb) ? 2u : 0u);                        \
+    } else if (!(done & 1u)) {                                                                   \
+        d.x = de_fast_epilogue(r2.x, dr.x);                                                      \
+        if (fast_suspect_inside<kBand>(s, r2.x, ampa)) suspect |= 1u;                            \
+    } else {                                                                                     \
+        d.y = de_fast_epilogue(r2.y, dr.y);                                                      \
+        if (fast_suspect_inside<kBand>(s, r2.y, ampb)) suspect |= 2u;                            \
     }
 
 template <bool kBand>
@@ -513,11 +556,7 @@ __device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float
         const float2 z2 = L::mul(zz, zz);
         const float2 w2 = L::fma(zx, zx, L::mul(zy, zy));
         r2 = L::add(w2, z2);
-        if ((r2.x > bail2) | (r2.y > bail2)) {
-            CTC_PAIR_ESCAPE(x, 1u, ampa)
-            CTC_PAIR_ESCAPE(y, 2u, ampb)
-            if (done == 3u) return;
-        }
+        CTC_PAIR_RADIUS_TEST()
         float2 g, A, iw;
         dr = p8_dr<float2>(r2, dr, g);
         if (--left == 0u) break;
@@ -525,15 +564,7 @@ __device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float
         amp_step<kBand>(ampa, g.x, A.x, iw.x);
         amp_step<kBand>(ampb, g.y, A.y, iw.y);
     }
-    // the halves that ran all max_iters iterations
-    if (!(done & 1u)) {
-        d.x = de_fast_epilogue(r2.x, dr.x);
-        if (fast_suspect_inside<kBand>(s, r2.x, ampa)) suspect |= 1u;
-    }
-    if (!(done & 2u)) {
-        d.y = de_fast_epilogue(r2.y, dr.y);
-        if (fast_suspect_inside<kBand>(s, r2.y, ampb)) suspect |= 2u;
-    }
+    CTC_PAIR_TAIL()
 }
 
 // FAST power-8 DE of two arbitrary points.  Bit k of `suspect`: the result of half k needs the exact path.
@@ -561,29 +592,23 @@ __device__ __forceinline__ ColumnFastP8 column_fast_p8(float px, float py) {
 }
 
 template <bool kBand>
-__device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeDev& s, float px_, float py_, float2 pz,
-                                                                    const ColumnFastP8& c, uint32_t& suspect) {
+__device__ __forceinline__ void p8_column_pair_impl(const ShapeDev& s, float px_, float py_, float2 pz, const ColumnFastP8& c,
+                                                    float2& d, uint32_t& suspect) {
     using L = Lanes<float2>;
     const float bail2 = s.bail2;
     const float2 px = L::bc(px_), py = L::bc(py_);
-    float2 d = make_float2(0.0f, 0.0f), dr = L::bc(1.0f);
+    float2 dr = L::bc(1.0f);
     uint32_t done = 0u, left = s.max_iters;
     Amp ampa = amp_init(), ampb = amp_init();
-    suspect = 0u;
     const float2 z2 = L::mul(pz, pz);
     const float2 w2 = L::bc(c.w2);
     float2 r2 = L::add(w2, z2);
-    if ((r2.x > bail2) | (r2.y > bail2)) {
-        CTC_PAIR_ESCAPE(x, 1u, ampa)
-        CTC_PAIR_ESCAPE(y, 2u, ampb)
-        if (done == 3u) return d;
-    }
+    CTC_PAIR_RADIUS_TEST()
     float2 g;
     dr = p8_dr<float2>(r2, dr, g);
     if (--left == 0u) {
-        if (!(done & 1u)) { d.x = de_fast_epilogue(r2.x, dr.x); if (fast_suspect_inside<kBand>(s, r2.x, ampa)) suspect |= 1u; }
-        if (!(done & 2u)) { d.y = de_fast_epilogue(r2.y, dr.y); if (fast_suspect_inside<kBand>(s, r2.y, ampb)) suspect |= 2u; }
-        return d;
+        CTC_PAIR_TAIL()
+        return;
     }
     float2 A, Zhn;
     p8_elevation<float2>(pz, z2, L::bc(c.w), w2, A, Zhn);
@@ -593,9 +618,19 @@ __device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeD
     amp_step<kBand>(ampa, g.x, A.x, c.iw);
     amp_step<kBand>(ampb, g.y, A.y, c.iw);
     p8_pair_loop<kBand>(s, px, py, pz, zx, zy, zz, dr, ampa, ampb, left, d, done, suspect);
+}
+
+template <bool kBand>
+__device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeDev& s, float px_, float py_, float2 pz,
+                                                                    const ColumnFastP8& c, uint32_t& suspect) {
+    float2 d = make_float2(0.0f, 0.0f);
+    suspect = 0u;
+    p8_column_pair_impl<kBand>(s, px_, py_, pz, c, d, suspect);
     return d;
 }
 #undef CTC_PAIR_ESCAPE
+#undef CTC_PAIR_RADIUS_TEST
+#undef CTC_PAIR_TAIL
 
 // FAST generic-power DE of one sample (config 4's P = 2, 4, 16, ...): trig-free complex binary powers
 //   (z + i w)^P = r^P (cos P.theta + i sin P.theta),   ((x + i y)/w)^P = cos P.phi + i sin P.phi

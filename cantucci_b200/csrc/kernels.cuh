@@ -169,19 +169,21 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         // the sample positions by an ulp (buffer.rs:79-80 is a multiply, then an add).
         float vza = __fmul_rn((float)z, inv_r), vzb = __fmul_rn((float)(z + 4u), inv_r);
         float* out = grid + ((size_t)x * n + y) * n + z;                         // util/grid.rs:45-48
-        uint32_t row_shift = (lane >> 2) << 2;          // this lane's row (xl,yl) nibble in a brick ballot
-        asm volatile("" : "+r"(row_shift));             // keep it in a register (no S2R re-read per step)
         const float gs2 = g.s[2], ga2 = g.across[2];
         const uint32_t j_row = (x * n + y) * n + (zb << lgL);     // plane bit of this lane's row at the block's first z
         const bool writer = sign_stride != 0u && (lane & 3u) == 0u;
         // the on-axis special case of the column paths is tested once per warp, not once per sample
         const bool any_axis = (kFast || kVariant == kVarP8) && __any_sync(0xffffffffu, px == 0.0f && py == 0.0f);
-        // 4 steps fill one 32-bit row word of the sign plane, which is then OR-ed in (two atomics).
+        // 4 steps fill one 32-bit row word of the sign plane, which is then OR-ed in (two atomics).  Every lane
+        // pushes the sign bits of its own samples into `acc` (one funnel shift each: no ballots in the walk);
+        // after the 4 steps the 8 bits are spread to their places 8 j + 4 half + zl of the row word and the
+        // four lanes of a row OR their parts together (two shuffles per 256 samples).
         // DE_PAIR sets `float2 d` from (px, py, pz.x) and (px, py, pz.y).
+        const uint32_t zl = lane & 3u;
 #define CTC_K1_STEPS(...)                                                                          \
         _Pragma("unroll 1")                                                                        \
         for (uint32_t h = 0; h < (1u << lgw); ++h) {                                               \
-            uint32_t word = 0;                                                                     \
+            uint32_t acc = 0;                                                                      \
             _Pragma("unroll 1")                                                                    \
             for (int j = 0; j < 4; ++j) {                                                          \
                 const float2 pz = make_float2(__fadd_rn(gs2, __fmul_rn(ga2, vza)),                 \
@@ -191,18 +193,25 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
                 out[0] = d.x;                                                                      \
                 out[4] = d.y;                                                                      \
                 out += 8;                                                                          \
-                const uint32_t ba = __ballot_sync(0xffffffffu, __float_as_uint(d.x) >> 31);        \
-                const uint32_t bb = __ballot_sync(0xffffffffu, __float_as_uint(d.y) >> 31);        \
-                const uint32_t byte = ((ba >> row_shift) & 15u) | (((bb >> row_shift) & 15u) << 4); \
-                word = (word >> 8) | (byte << 24);                   /* byte j -> bits [8j, 8j+8) */ \
+                acc = __funnelshift_l(__float_as_uint(d.x), acc, 1);     /* push k = 2 j + half */ \
+                acc = __funnelshift_l(__float_as_uint(d.y), acc, 1);                               \
                 vza = __fadd_rn(vza, dvz8);                                                        \
                 vzb = __fadd_rn(vzb, dvz8);                                                        \
             }                                                                                      \
-            if (writer && word != 0u) {                                                            \
-                const uint32_t j0 = j_row + (h << 5);                                              \
-                const uint32_t sft = j0 & 31u;                                                     \
-                atomicOr(&plane[j0 >> 5], word << sft);                                            \
-                if (sft) atomicOr(&plane[(j0 >> 5) + 1u], word >> (32u - sft));                    \
+            if (sign_stride != 0u) {                                                               \
+                uint32_t t = __brev(acc) >> 24;                          /* push k at bit k */     \
+                t = (t | (t << 12)) & 0x000F000Fu;                                                 \
+                t = (t | (t << 6)) & 0x03030303u;                                                  \
+                t = (t | (t << 3)) & 0x11111111u;                        /* push k at bit 4 k */   \
+                t <<= zl;                                                                          \
+                t |= __shfl_xor_sync(0xffffffffu, t, 1);                                           \
+                const uint32_t word = t | __shfl_xor_sync(0xffffffffu, t, 2);                      \
+                if (writer && word != 0u) {                                                        \
+                    const uint32_t j0 = j_row + (h << 5);                                          \
+                    const uint32_t sft = j0 & 31u;                                                 \
+                    atomicOr(&plane[j0 >> 5], word << sft);                                        \
+                    if (sft) atomicOr(&plane[(j0 >> 5) + 1u], word >> (32u - sft));                \
+                }                                                                                  \
             }                                                                                      \
         }
         if (any_axis) {
@@ -214,9 +223,9 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
             CTC_K1_STEPS(
                 uint32_t susp;
                 d = mandelbulb_de_fast_p8_column_pair<true>(sh, px, py, pz, col, susp);
-                const uint32_t ma = __ballot_sync(0xffffffffu, susp & 1u);
-                const uint32_t mb = __ballot_sync(0xffffffffu, susp & 2u);
-                if (ma | mb) {      /* rare: queue the suspects for the exact re-evaluation */
+                if (__any_sync(0xffffffffu, susp != 0u)) {   /* rare: queue the suspects for the exact re-evaluation */
+                    const uint32_t ma = __ballot_sync(0xffffffffu, susp & 1u);
+                    const uint32_t mb = __ballot_sync(0xffffffffu, susp & 2u);
                     uint32_t base = 0;
                     if (lane == 0u) base = atomicAdd(sl.count, (unsigned int)(__popc(ma) + __popc(mb)));
                     base = __shfl_sync(0xffffffffu, base, 0);
