@@ -548,13 +548,12 @@ def ours_main(args):
         # ---- extraction: HBM roofline of the byte-moving kernels (E1 classify, E2b prefix, E4 quads) -------------
         V, Q = info["nv_loc"], info["ni_loc"] // 6
         ext_bytes = len(local_spans) * n3 / 8.0 + 28.0 * V + 24.0 * Q           # SURVEY 8d, fused form: sign bits + vertices + indices
-        ext_ms = kernel_ms["classify"] + kernel_ms["apply_prefix"] + kernel_ms["quads"]
+        ext_ms = kernel_ms["classify_count"] + kernel_ms["span_scan"] + kernel_ms["emit_lists"] + kernel_ms["quads"]
         roofline_extraction = {
-            "bound": "hbm", "kernels": "classify_kernel + apply_prefix_kernel + quad_kernel (E1 + E2b + E4), per volume, serial kernels",
+            "bound": "hbm", "kernels": "classify_count + span_scan + emit_lists + quad_kernel (E1, E2a, E2b, E4), per volume, serial kernels",
             "algorithmic_bytes": ext_bytes, "formula": "n^3/8 per span (sign bit-plane) + 28 V + 24 Q (SURVEY 8d, fused form)",
             "ms": ext_ms, "achieved": ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
             "frac": ext_bytes / (ext_ms * 1e-3) / 1e9 / hbm_gbs if ext_ms > 0 else None, "peak_source": hbm_src,
-            "scan_chunks_ms": kernel_ms["scan_chunks"],
         }
         whole = None
         if flops_e3 is not None:

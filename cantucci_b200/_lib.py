@@ -229,7 +229,7 @@ class Context:
     def synchronize(self):
         self.check(lib().ctc_ctx_synchronize(self._h))
 
-    KERNELS = ("sample_grids", "fixup_suspects", "classify", "scan_chunks", "apply_prefix", "vertex", "quads")
+    KERNELS = ("sample_grids", "fixup_suspects", "classify_count", "span_scan", "emit_lists", "vertex", "quads")
 
     def set_coalescing(self, enable: bool):
         self.check(lib().ctc_ctx_set_coalescing(self._h, 1 if enable else 0))

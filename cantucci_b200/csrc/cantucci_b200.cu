@@ -91,7 +91,7 @@ struct ctc_ctx {
 
     // workspace
     DevBuf suspects, suspect_count;               // fast mode: K1's suspect lists (double-buffered like the grids)
-    DevBuf geom, grids, sign_bits, m_active, m_ex, m_ey, m_ez, chunk_counts, chunk_pre, word_vpre, word_qpre, cell_of, state;
+    DevBuf geom, grids, sign_bits, m_active, word_vpre, cell_of, quad_of, span_first, neg8, chunk_cnt, span_tot, span_pre, state;
     DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
     DevBuf pts_in, pts_out;
     PinnedBuf h_geom, h_state, h_tables;
@@ -248,12 +248,11 @@ GroupPlan plan_groups(const ctc_ctx* ctx, uint32_t R, uint32_t lg, size_t nspans
         const size_t quarter = (nspans + 3) / 4;
         if (quarter >= 64 && g > quarter) g = quarter;
     }
-    const size_t max_by_cells = (size_t)1 << (31 - 3 * lg > 0 ? 31 - 3 * lg : 0);  // span<<lg3 | cell fits u32
+    // span << 3 lg | cell fits 30 bits (two more carry a quad's edge; the chunk scan's status word keeps 30 bits
+    // of vertices and 32 of quads)
+    const size_t max_by_cells = (size_t)1 << (30 - 3 * lg > 0 ? 30 - 3 * lg : 0);
     if (g > max_by_cells) g = max_by_cells;
     if (g > 32768) g = 32768;                                                      // gridDim.y
-    // chunk-count scan is a single CTA: keep it short
-    const size_t max_by_chunks = (1u << 20) / p.chunks_per_span;
-    if (g > max_by_chunks && max_by_chunks >= 1) g = max_by_chunks;
     if (g > nspans) g = nspans;
     if (g < 1) g = 1;
     p.group_spans = (uint32_t)g;
@@ -398,9 +397,9 @@ int de_batch_impl(ctc_ctx* ctx, const ctc_shape* shape, const float* d_xyz, size
 
 template <bool kFast, int kVariant>
 void launch_vertex(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, const float* grids, size_t stride, uint32_t R,
-                   uint32_t lg, const uint32_t* cell_of, uint32_t cell_cap, MeshState* st, uint32_t span0, float* out_v,
+                   uint32_t lg, const uint32_t* cell_of, uint32_t cell_cap, uint8_t* neg8, MeshState* st, uint32_t span0, float* out_v,
                    unsigned long long vcap, unsigned blocks, cudaStream_t stream) {
-    vertex_kernel<kFast, kVariant><<<blocks, kThreads, 0, stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap,
+    vertex_kernel<kFast, kVariant><<<blocks, kThreads, 0, stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap, neg8,
                                                                          st, span0, out_v, vcap);
     ctx->launches++;
 }
@@ -452,13 +451,18 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
     const bool two_streams = (nspans > G) && ctx->overlap;
     const size_t nbuf = two_streams ? 2 : 1;
     CK(ctx->grids.ensure(nbuf * G * gp.n3 * sizeof(float)));
-    CK(ctx->m_active.ensure(words * 4)); CK(ctx->m_ex.ensure(words * 4)); CK(ctx->m_ey.ensure(words * 4));
-    CK(ctx->m_ez.ensure(words * 4));
+    CK(ctx->m_active.ensure(words * 4));
     const uint32_t sign_stride = (uint32_t)((gp.n3 + 31) / 32 + 1);
     CK(ctx->sign_bits.ensure(nbuf * G * (size_t)sign_stride * 4));
-    CK(ctx->word_vpre.ensure(words * 4)); CK(ctx->word_qpre.ensure(words * 4));
-    CK(ctx->chunk_counts.ensure(chunks * sizeof(uint2))); CK(ctx->chunk_pre.ensure(chunks * sizeof(uint2)));
+    CK(ctx->word_vpre.ensure(words * 4));
+    // quads: at most three per active cell, and never more than the caller's index buffer holds
+    const size_t quad_room = 3 * (size_t)cell_cap, quad_out = icap / 6;
+    const uint32_t quad_cap = (uint32_t)(quad_room < quad_out ? quad_room : (quad_out < 0xFFFFFFFFull ? quad_out : 0xFFFFFFFFull));
     CK(ctx->cell_of.ensure((size_t)(cell_cap ? cell_cap : 1) * 4));
+    CK(ctx->neg8.ensure((size_t)(cell_cap ? cell_cap : 1)));
+    CK(ctx->quad_of.ensure((size_t)(quad_cap ? quad_cap : 1) * 4));
+    CK(ctx->span_first.ensure(G * 4));
+    CK(ctx->chunk_cnt.ensure(chunks * sizeof(uint2))); CK(ctx->span_tot.ensure(G * 8)); CK(ctx->span_pre.ensure(G * sizeof(uint2)));
     const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
     const int variant = shape_variant(shape);
     // fast mode, power 8: K1 queues the samples whose sign cannot be trusted; the extraction stream
@@ -469,7 +473,8 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         CK(ctx->suspects.ensure(nbuf * list_cap * sizeof(uint2)));
         CK(ctx->suspect_count.ensure(2 * sizeof(unsigned int)));
     }
-    Masks m{ctx->m_active.as<uint32_t>(), ctx->m_ex.as<uint32_t>(), ctx->m_ey.as<uint32_t>(), ctx->m_ez.as<uint32_t>()};
+    const ExtractionLists ls{ctx->m_active.as<uint32_t>(), ctx->word_vpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
+                             ctx->quad_of.as<uint32_t>(), ctx->span_first.as<uint32_t>(), ctx->neg8.as<uint8_t>(), cell_cap, quad_cap};
 
     const unsigned vblocks = (unsigned)ctx->num_sms * 8u;
     // Launch groups.  With the copy pipeline on, the first groups are small (64, 128, 256, ... spans)
@@ -548,36 +553,34 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
             CK(cudaEventRecord(ctx->k1_done[gi], sA));
             CK(cudaStreamWaitEvent(sE, ctx->k1_done[gi], 0));
         }
-        dim3 cgrid(gp.chunks_per_span, cnt);
-        {   // pass 2: (fast mode: sign repair,) classify, scan, vertices
+        {   // pass 2: (fast mode: sign repair,) classify + compact, vertices
             PassTimer t(ctx, 1, sE);
             if (listed) {
                 PassTimer k(ctx, 3 + CTC_K_FIXUP, sE);
                 launch_fixup(ctx, sh, variant, geom, R, grids, gp.n3, sign_bits, sign_stride, sl, st, sE);
             }
+            dim3 cgrid(gp.chunks_per_span, cnt);
             {
                 PassTimer k(ctx, 3 + CTC_K_CLASSIFY, sE);
-                classify_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.words_per_span,
-                                                            gp.chunk_words, m, ctx->chunk_counts.as<uint2>());
+                CK(cudaMemsetAsync(ctx->span_tot.p, 0, (size_t)cnt * 8, sE));
+                classify_count_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.chunk_words,
+                                                                  ctx->chunk_cnt.as<uint2>(), ctx->span_tot.as<unsigned long long>());
             }
             {
                 PassTimer k(ctx, 3 + CTC_K_SCAN, sE);
-                scan_chunks_kernel<<<1, kScanThreads, 0, sE>>>(
-                    ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), cnt * gp.chunks_per_span, gp.chunks_per_span,
-                    (uint32_t)s0, cnt, reinterpret_cast<unsigned long long*>(d_v_off),
-                    reinterpret_cast<unsigned long long*>(d_i_off), (unsigned long long)vcap, (unsigned long long)icap, st,
-                    pipeline ? ctx->progress_d + 2 * gi : nullptr);
+                span_scan_kernel<<<1, kScanThreads, 0, sE>>>(
+                    ctx->span_tot.as<unsigned long long>(), ctx->span_pre.as<uint2>(), ls.span_first, (uint32_t)s0, cnt,
+                    reinterpret_cast<unsigned long long*>(d_v_off), reinterpret_cast<unsigned long long*>(d_i_off),
+                    (unsigned long long)vcap, (unsigned long long)icap, st, pipeline ? ctx->progress_d + 2 * gi : nullptr);
             }
             {
                 PassTimer k(ctx, 3 + CTC_K_PREFIX, sE);
-                apply_prefix_kernel<<<cgrid, kThreads, 0, sE>>>(m, ctx->chunk_counts.as<uint2>(), ctx->chunk_pre.as<uint2>(), gp.words_per_span,
-                                                                gp.chunk_words, 3 * lg, ctx->word_vpre.as<uint32_t>(),
-                                                                ctx->word_qpre.as<uint32_t>(), ctx->cell_of.as<uint32_t>(),
-                                                                cell_cap);
+                emit_lists_kernel<<<cgrid, kThreads, 0, sE>>>(sign_bits, sign_stride, R, lg, gp.words_per_span, gp.chunk_words,
+                                                              ctx->chunk_cnt.as<uint2>(), ctx->span_pre.as<uint2>(), ls);
             }
             ctx->launches += 3;
             PassTimer k(ctx, 3 + CTC_K_VERTEX, sE);
-#define CALL(F, V) launch_vertex<F, V>(ctx, sh, geom, grids, gp.n3, R, lg, ctx->cell_of.as<uint32_t>(), cell_cap, st, \
+#define CALL(F, V) launch_vertex<F, V>(ctx, sh, geom, grids, gp.n3, R, lg, ls.cell_of, cell_cap, ls.neg8, st, \
                                        (uint32_t)s0, reinterpret_cast<float*>(d_v), (unsigned long long)vcap, vblocks, sE)
             DISPATCH(fast, variant, CALL);
 #undef CALL
@@ -585,15 +588,9 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         {   // pass 3
             PassTimer t(ctx, 2, sE);
             if (pipeline && ctx->wire_quads)
-                quad_kernel<true><<<vblocks, kThreads, 0, sE>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
-                                                                grids, gp.n3, R, lg, gp.words_per_span,
-                                                                ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
-                                                                (unsigned long long)icap);
+                quad_kernel<true><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st, d_idx, (unsigned long long)icap);
             else
-                quad_kernel<false><<<vblocks, kThreads, 0, sE>>>(m, ctx->word_vpre.as<uint32_t>(), ctx->word_qpre.as<uint32_t>(),
-                                                                 grids, gp.n3, R, lg, gp.words_per_span,
-                                                                 ctx->cell_of.as<uint32_t>(), cell_cap, st, d_idx,
-                                                                 (unsigned long long)icap);
+                quad_kernel<false><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st, d_idx, (unsigned long long)icap);
             ctx->launches++;
         }
         if (pipeline) CK(cudaEventRecord(ctx->group_events[gi], sE));
@@ -684,8 +681,8 @@ void ctc_ctx_destroy(ctc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->m_ex, &c->m_ey, &c->m_ez, &c->sign_bits, &c->chunk_counts,
-                      &c->chunk_pre, &c->word_vpre, &c->word_qpre, &c->cell_of, &c->state, &c->out_v, &c->out_idx,
+    for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->sign_bits, &c->word_vpre, &c->cell_of, &c->quad_of,
+                      &c->span_first, &c->neg8, &c->chunk_cnt, &c->span_tot, &c->span_pre, &c->state, &c->out_v, &c->out_idx,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
     c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release();

@@ -3,12 +3,12 @@
 //   K1  sample_grids_kernel   pass 1 of naive_surface_nets (mesh/buffer.rs:77-83); also emits the
 //                             sign bit-plane (1 bit per sample, reference layout)
 //   K3  de_batch_kernel       Shape::batch_min_distance_from (shape/mod.rs:89)
-//   E1  classify_kernel       cell / edge sign classification from the bit-plane, 32 cells per
-//                             thread (buffer.rs:116-147, 299-350)
-//   E2a scan_chunks_kernel    order-preserving prefix over chunk counts
-//   E2b apply_prefix_kernel   per-word prefixes + compacted active-cell list
+//   E1  classify_count_kernel cell / edge sign classification from the bit-plane, 32 cells per thread
+//                             (buffer.rs:116-147, 299-350): counts per chunk and span
+//   E2a span_scan_kernel      order-preserving prefix over span totals, offset tables
+//   E2b emit_lists_kernel     active-cell list, quad list, rank-query tables
 //   E3  vertex_kernel         per-active-cell vertex (buffer.rs:150-274)
-//   E4  quad_kernel           per-edge quads, reference emission order (buffer.rs:288-372)
+//   E4  quad_kernel           one thread per quad, reference emission order (buffer.rs:288-372)
 //   N1  ray_march_kernel      get_focii's sphere tracing (mesh/mod.rs:229-241)
 //   +   iteration_stats_kernel / fma_peak_kernel: measurement aids for bench.py
 //
@@ -50,7 +50,7 @@ struct MeshState {
 };
 
 constexpr int kThreads = 256;
-constexpr uint32_t kMaxChunkWords = 256;  // one word per thread in E2b
+constexpr uint32_t kMaxChunkWords = 256;  // one word per thread in E1+E2
 
 // ---------------------------------------------------------------------------
 // sample index -> lattice coordinates
@@ -358,139 +358,131 @@ __device__ __forceinline__ void block_exclusive_scan2(uint32_t v, uint32_t q, ui
 }
 
 // ---------------------------------------------------------------------------
-// E1: classification from the sign bit-plane.  One thread per word of 32 cells
-// (cube(R) order), one CTA per chunk of <= 256 words; gridDim = (chunks_per_span,
-// spans).  For R >= 32 a word is 32 z-consecutive cells of one (x,y) row: its 8
-// corner sign words are 33-bit windows of four plane rows (funnel shifts), and
-// the active / edge masks are a handful of bitwise ops.
+// E1 / E2: classification from the sign bit-plane and order-preserving compaction.
+//
+// A word is 32 cells in cube(R) order; for R >= 32 that is 32 z-consecutive cells of one (x,y) row: its 8
+// corner sign words are 33-bit windows of four plane rows (funnel shifts), and the active / edge masks are a
+// handful of bitwise ops (buffer.rs:116-147, 299-350).  Words whose plane words are all 0 or all 1 (most of
+// a volume) take a short cut.  A chunk is <= 256 consecutive words of one span, one CTA.
+//
+// Three short, wide kernels (no CTA ever waits for another):
+//   E1  classify_count_kernel  (vertices, quads) per chunk, summed per span with one 64-bit atomic per chunk
+//   E2a span_scan_kernel       prefix over the group's spans (hundreds), offset tables, totals
+//   E2b emit_lists_kernel      chunks WITH active cells (~1/4 of a typical volume) recompute their masks and
+//                              write the active-cell list, the quad list and the rank-query tables in place
 // ---------------------------------------------------------------------------
-struct Masks {
-    uint32_t* active;  // cell crosses the surface (buffer.rs:130-141)
-    uint32_t* ex;      // +x edge from the cell's lower corner emits a quad (:302)
-    uint32_t* ey;      // +y edge (:326)
-    uint32_t* ez;      // +z edge (:350)
-};
-
 __device__ __forceinline__ uint32_t plane_bit(const uint32_t* __restrict__ plane, uint32_t j) {
     return (plane[j >> 5] >> (j & 31u)) & 1u;
 }
 
-// 33 consecutive plane bits starting at j: lo = bits j..j+31, returns bit j+32 in hi
-__device__ __forceinline__ uint32_t plane_window(const uint32_t* __restrict__ plane, uint32_t j, uint32_t& hi) {
-    const uint32_t w0 = plane[j >> 5], w1 = plane[(j >> 5) + 1u];
-    const uint32_t s = j & 31u;
-    hi = (w1 >> s) & 1u;
-    return __funnelshift_r(w0, w1, s);
-}
-
-__global__ void __launch_bounds__(kThreads)
-classify_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, uint32_t R, uint32_t lg,
-                uint32_t words_per_span, uint32_t chunk_words, Masks m, uint2* __restrict__ chunk_counts) {
-    const uint32_t span = blockIdx.y, chunk = blockIdx.x;
-    const uint32_t t = threadIdx.x;
-    const uint32_t n = R + 1u, R3 = R << (2 * lg);
-    const uint32_t* __restrict__ plane = sign_bits + (size_t)span * sign_stride;
-    uint32_t ma = 0, mx = 0, my = 0, mz = 0;
-    if (t < chunk_words) {
-        const uint32_t word = chunk * chunk_words + t;
-        const uint32_t c0 = word << 5;
-        if (lg >= 5) {
-            const uint32_t x = c0 >> (2 * lg), y = (c0 >> lg) & (R - 1u), z0 = c0 & (R - 1u);
-            const uint32_t j = (x * n + y) * n + z0;
-            uint32_t h0, h2, h4, h6;
-            const uint32_t s0 = plane_window(plane, j, h0);                 // corner 0 (x, y, z)
-            const uint32_t s2 = plane_window(plane, j + n, h2);             // corner 2 (x, y+1, z)
-            const uint32_t s4 = plane_window(plane, j + n * n, h4);         // corner 4 (x+1, y, z)
-            const uint32_t s6 = plane_window(plane, j + n * n + n, h6);     // corner 6 (x+1, y+1, z)
-            const uint32_t s1 = (s0 >> 1) | (h0 << 31), s3 = (s2 >> 1) | (h2 << 31);   // dz = 1 corners
-            const uint32_t s5 = (s4 >> 1) | (h4 << 31), s7 = (s6 >> 1) | (h6 << 31);
-            const uint32_t any = s0 | s1 | s2 | s3 | s4 | s5 | s6 | s7;
-            const uint32_t all = s0 & s1 & s2 & s3 & s4 & s5 & s6 & s7;
-            ma = any & ~all;
-            const uint32_t zm = z0 == 0u ? ~1u : ~0u;                       // z > 0
-            mx = (y > 0u) ? ((s0 ^ s4) & zm) : 0u;                          // y > 0 && z > 0 (:302)
-            my = (x > 0u) ? ((s0 ^ s2) & zm) : 0u;                          // x > 0 && z > 0 (:326)
-            mz = (x > 0u && y > 0u) ? (s0 ^ s1) : 0u;                       // x > 0 && y > 0 (:350)
-        } else {
-            for (uint32_t b = 0; b < 32u; ++b) {
-                const uint32_t c = c0 + b;
-                if (c >= R3) break;
-                const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
-                const uint32_t j = (x * n + y) * n + z;
-                const uint32_t s0 = plane_bit(plane, j), s1 = plane_bit(plane, j + 1u);
-                const uint32_t s2 = plane_bit(plane, j + n), s3 = plane_bit(plane, j + n + 1u);
-                const uint32_t s4 = plane_bit(plane, j + n * n), s5 = plane_bit(plane, j + n * n + 1u);
-                const uint32_t s6 = plane_bit(plane, j + n * n + n), s7 = plane_bit(plane, j + n * n + n + 1u);
-                const uint32_t sum = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
-                ma |= (uint32_t)(sum != 0u && sum != 8u) << b;
-                mx |= (uint32_t)(y > 0u && z > 0u && s0 != s4) << b;
-                my |= (uint32_t)(x > 0u && z > 0u && s0 != s2) << b;
-                mz |= (uint32_t)(x > 0u && y > 0u && s0 != s1) << b;
-            }
+// masks of word `word` (cells 32 word .. 32 word + 31) of a span
+__device__ __forceinline__ void word_masks(const uint32_t* __restrict__ plane, uint32_t R, uint32_t lg, uint32_t word,
+                                           uint32_t& ma, uint32_t& mx, uint32_t& my, uint32_t& mz) {
+    const uint32_t n = R + 1u;
+    const uint32_t c0 = word << 5;
+    ma = 0u; mx = 0u; my = 0u; mz = 0u;
+    if (lg >= 5) {
+        const uint32_t x = c0 >> (2 * lg), y = (c0 >> lg) & (R - 1u), z0 = c0 & (R - 1u);
+        // the four plane rows of the word's corners: (x, y), (x, y+1), (x+1, y), (x+1, y+1); 33 bits from j each
+        const uint32_t j0 = (x * n + y) * n + z0, j2 = j0 + n, j4 = j0 + n * n, j6 = j4 + n;
+        const uint32_t a0 = plane[j0 >> 5], b0 = plane[(j0 >> 5) + 1u], a2 = plane[j2 >> 5], b2 = plane[(j2 >> 5) + 1u];
+        const uint32_t a4 = plane[j4 >> 5], b4 = plane[(j4 >> 5) + 1u], a6 = plane[j6 >> 5], b6 = plane[(j6 >> 5) + 1u];
+        const uint32_t any_w = a0 | b0 | a2 | b2 | a4 | b4 | a6 | b6, all_w = a0 & b0 & a2 & b2 & a4 & b4 & a6 & b6;
+        if (any_w == 0u || all_w == 0xffffffffu) return;      // uniform plane words: no sign change in the word
+        const uint32_t s0 = __funnelshift_r(a0, b0, j0 & 31u), h0 = (b0 >> (j0 & 31u)) & 1u;     // corner 0 (x, y, z)
+        const uint32_t s2 = __funnelshift_r(a2, b2, j2 & 31u), h2 = (b2 >> (j2 & 31u)) & 1u;     // corner 2 (x, y+1, z)
+        const uint32_t s4 = __funnelshift_r(a4, b4, j4 & 31u), h4 = (b4 >> (j4 & 31u)) & 1u;     // corner 4 (x+1, y, z)
+        const uint32_t s6 = __funnelshift_r(a6, b6, j6 & 31u), h6 = (b6 >> (j6 & 31u)) & 1u;     // corner 6 (x+1, y+1, z)
+        const uint32_t s1 = (s0 >> 1) | (h0 << 31), s3 = (s2 >> 1) | (h2 << 31);   // dz = 1 corners
+        const uint32_t s5 = (s4 >> 1) | (h4 << 31), s7 = (s6 >> 1) | (h6 << 31);
+        const uint32_t any = s0 | s1 | s2 | s3 | s4 | s5 | s6 | s7;
+        const uint32_t all = s0 & s1 & s2 & s3 & s4 & s5 & s6 & s7;
+        ma = any & ~all;
+        const uint32_t zm = z0 == 0u ? ~1u : ~0u;                       // z > 0
+        mx = (y > 0u) ? ((s0 ^ s4) & zm) : 0u;                          // y > 0 && z > 0 (:302)
+        my = (x > 0u) ? ((s0 ^ s2) & zm) : 0u;                          // x > 0 && z > 0 (:326)
+        mz = (x > 0u && y > 0u) ? (s0 ^ s1) : 0u;                       // x > 0 && y > 0 (:350)
+    } else {
+        const uint32_t R3 = R << (2 * lg);
+        for (uint32_t b = 0; b < 32u; ++b) {
+            const uint32_t c = c0 + b;
+            if (c >= R3) break;
+            const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
+            const uint32_t j = (x * n + y) * n + z;
+            const uint32_t s0 = plane_bit(plane, j), s1 = plane_bit(plane, j + 1u);
+            const uint32_t s2 = plane_bit(plane, j + n), s3 = plane_bit(plane, j + n + 1u);
+            const uint32_t s4 = plane_bit(plane, j + n * n), s5 = plane_bit(plane, j + n * n + 1u);
+            const uint32_t s6 = plane_bit(plane, j + n * n + n), s7 = plane_bit(plane, j + n * n + n + 1u);
+            const uint32_t sum = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
+            ma |= (uint32_t)(sum != 0u && sum != 8u) << b;
+            mx |= (uint32_t)(y > 0u && z > 0u && s0 != s4) << b;
+            my |= (uint32_t)(x > 0u && z > 0u && s0 != s2) << b;
+            mz |= (uint32_t)(x > 0u && y > 0u && s0 != s1) << b;
         }
     }
-    // chunk totals
-    uint32_t v = __popc(ma), q = __popc(mx) + __popc(my) + __popc(mz);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
+}
+
+struct ExtractionLists {
+    uint32_t* active;      // cell crosses the surface (buffer.rs:130-141), one bit per cell
+    uint32_t* word_vpre;   // group-local vertex slot of the first active cell at/after each word
+    uint32_t* cell_of;     // [cell_cap] span << 3 lg | cell of every active cell, cube(R) order
+    uint32_t* quad_of;     // [quad_cap] (span << 3 lg | owner cell) | edge << 30, emission order
+    uint32_t* span_first;  // [spans of the group] group-local slot of the span's first vertex
+    uint8_t*  neg8;        // [cell_cap] written by E3: dists[lower corner of the cell] < 0.0 (winding, buffer.rs:310)
+    uint32_t cell_cap, quad_cap;
+};
+
+// E1: counts.  gridDim = (chunks_per_span, spans); one thread per word.  Writes (active cells, quads) of every
+// chunk and adds them to the span's total ({vertices:32 | quads:32} in one 64-bit atomic; zeroed per group).
+__global__ void __launch_bounds__(kThreads)
+classify_count_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, uint32_t R, uint32_t lg,
+                      uint32_t chunk_words, uint2* __restrict__ chunk_cnt, unsigned long long* __restrict__ span_tot) {
+    const uint32_t span = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    uint32_t ma = 0, mx = 0, my = 0, mz = 0;
+    if (t < chunk_words) word_masks(sign_bits + (size_t)span * sign_stride, R, lg, chunk * chunk_words + t, ma, mx, my, mz);
+    uint2* cnt = chunk_cnt + (size_t)span * gridDim.x + chunk;
+    // a chunk without an active cell (most of them) has no quads either: every quad-owning corner is an active cell
+    if (!__syncthreads_or(ma != 0u)) {
+        if (t == 0) *cnt = make_uint2(0u, 0u);
+        return;
     }
-    __shared__ uint32_t sv[kThreads / 32], sq[kThreads / 32];
-    if ((t & 31u) == 0u) { sv[t >> 5] = v; sq[t >> 5] = q; }
+    __shared__ uint32_t s_v, s_q;
+    if (t == 0) { s_v = 0u; s_q = 0u; }
     __syncthreads();
-    uint32_t tv = 0, tq = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) { tv += sv[w]; tq += sq[w]; }
-    if (t == 0) chunk_counts[(size_t)span * gridDim.x + chunk] = make_uint2(tv, tq);
-    // A chunk without an active cell is never looked at again (every quad-owning corner and every
-    // cell a rank query touches is active), so its four mask words per 32 cells are not written:
-    // ~3/4 of the chunks of a typical volume.
-    if (tv != 0u && t < chunk_words) {
-        const size_t o = (size_t)span * words_per_span + chunk * chunk_words + t;
-        m.active[o] = ma; m.ex[o] = mx; m.ey[o] = my; m.ez[o] = mz;
+    const uint32_t v = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(ma));
+    const uint32_t q = __reduce_add_sync(0xffffffffu, (uint32_t)(__popc(mx) + __popc(my) + __popc(mz)));
+    if ((t & 31u) == 0u && v) { atomicAdd(&s_v, v); atomicAdd(&s_q, q); }
+    __syncthreads();
+    if (t == 0) {
+        *cnt = make_uint2(s_v, s_q);
+        atomicAdd(span_tot + span, ((unsigned long long)s_v << 32) | (unsigned long long)s_q);
     }
 }
 
-// ---------------------------------------------------------------------------
-// E2a: exclusive scan over the group's chunk counts (single CTA), span offset
+// E2a: exclusive scan over the group's SPAN totals (one CTA; a group has a few hundred spans), span offset
 // tables, capacity check, running totals.
-// ---------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 16;   // consecutive chunks per thread and pass
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ chunk_pre, uint32_t nchunks,
-                   uint32_t chunks_per_span, uint32_t span0, uint32_t nspans_group,
-                   unsigned long long* __restrict__ v_off, unsigned long long* __restrict__ i_off,
-                   unsigned long long vcap, unsigned long long icap, MeshState* __restrict__ st,
-                   volatile unsigned long long* __restrict__ progress /* mapped pinned host memory or NULL */) {
+span_scan_kernel(const unsigned long long* __restrict__ span_tot, uint2* __restrict__ span_pre, uint32_t* __restrict__ span_first,
+                 uint32_t span0, uint32_t nspans_group,
+                 unsigned long long* __restrict__ v_off, unsigned long long* __restrict__ i_off,
+                 unsigned long long vcap, unsigned long long icap, MeshState* __restrict__ st,
+                 volatile unsigned long long* __restrict__ progress /* mapped pinned host memory or NULL */) {
     const unsigned long long base_v = st->total_v, base_q = st->total_q;
     uint32_t carry_v = 0, carry_q = 0;
-    for (uint32_t t0 = 0; t0 < nchunks; t0 += kScanThreads * kScanItems) {
-        const uint32_t i0 = t0 + threadIdx.x * kScanItems;
-        uint2 c[kScanItems];
-        uint32_t sv = 0, sq = 0;
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            c[k] = (i0 + k < nchunks) ? chunk_counts[i0 + k] : make_uint2(0u, 0u);
-            sv += c[k].x; sq += c[k].y;
-        }
+    for (uint32_t s0 = 0; s0 < nspans_group; s0 += kScanThreads) {
+        const uint32_t s = s0 + threadIdx.x;
+        const unsigned long long tot = s < nspans_group ? span_tot[s] : 0ull;
+        const uint32_t v = (uint32_t)(tot >> 32), q = (uint32_t)tot;
         uint32_t ev, eq, tv, tq;
-        block_exclusive_scan2<kScanThreads>(sv, sq, ev, eq, tv, tq);
-        uint32_t pv = carry_v + ev, pq = carry_q + eq;
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            const uint32_t i = i0 + k;
-            if (i < nchunks) {
-                chunk_pre[i] = make_uint2(pv, pq);
-                if (i % chunks_per_span == 0u) {
-                    const uint32_t s = span0 + i / chunks_per_span;
-                    v_off[s] = base_v + pv;
-                    i_off[s] = 6ull * (base_q + pq);
-                }
-            }
-            pv += c[k].x; pq += c[k].y;
+        block_exclusive_scan2<kScanThreads>(v, q, ev, eq, tv, tq);
+        if (s < nspans_group) {
+            const uint32_t pv = carry_v + ev, pq = carry_q + eq;
+            span_pre[s] = make_uint2(pv, pq);
+            span_first[s] = pv;
+            v_off[span0 + s] = base_v + pv;
+            i_off[span0 + s] = 6ull * (base_q + pq);
         }
         carry_v += tv; carry_q += tq;
     }
@@ -507,41 +499,44 @@ scan_chunks_kernel(const uint2* __restrict__ chunk_counts, uint2* __restrict__ c
     }
 }
 
-// ---------------------------------------------------------------------------
-// E2b: per-word prefixes (span-local vertex id base, group-local quad slot) and
-// the compacted list of active cells.  Same grid as E1; one word per thread.
-// ---------------------------------------------------------------------------
+// E2b: the chunks with active cells write everything at its final place: `active` masks + `word_vpre`
+// (GROUP-local vertex slot at each word) for the rank queries of E4, `cell_of` (compacted active cells, the
+// work list of E3), `quad_of` (one entry per quad in the reference's emission order, the work list of E4).
+// A chunk's prefix = its span's prefix + the counts of the span's preceding chunks (<= 31 of them at
+// R = 64): no chain between CTAs.  The masks are recomputed from the plane (L2 hits) rather than stored by E1.
 __global__ void __launch_bounds__(kThreads)
-apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_counts, const uint2* __restrict__ chunk_pre,
-                    uint32_t words_per_span, uint32_t chunk_words,
-                    uint32_t lg3 /* log2(R^3) */, uint32_t* __restrict__ word_vpre, uint32_t* __restrict__ word_qpre,
-                    uint32_t* __restrict__ cell_of, uint32_t cell_cap) {
-    const uint32_t span = blockIdx.y, chunk = blockIdx.x;
-    const uint32_t t = threadIdx.x;
-    if (chunk_counts[(size_t)span * gridDim.x + chunk].x == 0u) return;   // no active cell: masks were not written
-    const size_t o = (size_t)span * words_per_span + chunk * chunk_words + t;
-    uint32_t ma = 0, v = 0, q = 0;
-    if (t < chunk_words) {
-        ma = m.active[o];
-        v = __popc(ma);
-        q = __popc(m.ex[o]) + __popc(m.ey[o]) + __popc(m.ez[o]);
+emit_lists_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, uint32_t R, uint32_t lg,
+                  uint32_t words_per_span, uint32_t chunk_words, const uint2* __restrict__ chunk_cnt,
+                  const uint2* __restrict__ span_pre, ExtractionLists ls) {
+    const uint32_t span = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    const uint2* cnt = chunk_cnt + (size_t)span * gridDim.x;
+    if (cnt[chunk].x == 0u) return;        // uniform: nothing of this chunk is ever read
+    __shared__ uint32_t s_pre[2];
+    if (t < 32u) {
+        uint32_t pv = 0, pq = 0;
+        for (uint32_t c = t; c < chunk; c += 32u) { const uint2 k = cnt[c]; pv += k.x; pq += k.y; }
+        pv = __reduce_add_sync(0xffffffffu, pv); pq = __reduce_add_sync(0xffffffffu, pq);
+        if (t == 0) { const uint2 sp = span_pre[span]; s_pre[0] = sp.x + pv; s_pre[1] = sp.y + pq; }
     }
+    uint32_t ma = 0, mx = 0, my = 0, mz = 0;
+    if (t < chunk_words) word_masks(sign_bits + (size_t)span * sign_stride, R, lg, chunk * chunk_words + t, ma, mx, my, mz);
+    const uint32_t v = __popc(ma), q = __popc(mx) + __popc(my) + __popc(mz);
     uint32_t ev, eq, tv, tq;
-    block_exclusive_scan2<kThreads>(v, q, ev, eq, tv, tq);
-    if (t < chunk_words) {
-        const uint2 cp = chunk_pre[(size_t)span * gridDim.x + chunk];
-        const uint32_t span_v0 = chunk_pre[(size_t)span * gridDim.x].x;   // group-local slot of the span's first vertex
-        const uint32_t gv = cp.x + ev;                                    // group-local vertex slot
-        word_vpre[o] = gv - span_v0;                                      // span-local vertex id
-        word_qpre[o] = cp.y + eq;                                         // group-local quad slot
-        const uint32_t cell0 = (span << lg3) + ((chunk * chunk_words + t) << 5);
-        uint32_t k = 0;
-        while (ma) {
-            const uint32_t b = __ffs(ma) - 1;
-            ma &= ma - 1u;
-            if (gv + k < cell_cap) cell_of[gv + k] = cell0 + b;
-            ++k;
-        }
+    block_exclusive_scan2<kThreads>(v, q, ev, eq, tv, tq);       // (its barriers also publish s_pre)
+    if (t >= chunk_words) return;
+    const size_t o = (size_t)span * words_per_span + chunk * chunk_words + t;
+    uint32_t gv = s_pre[0] + ev, slot = s_pre[1] + eq;
+    ls.active[o] = ma;
+    ls.word_vpre[o] = gv;
+    const uint32_t cell0 = (span << (3 * lg)) + ((chunk * chunk_words + t) << 5);
+    for (uint32_t m = ma; m; m &= m - 1u, ++gv)
+        if (gv < ls.cell_cap) ls.cell_of[gv] = cell0 + (uint32_t)__ffs((int)m) - 1u;
+    // the quads owned by the word's cells, corner by corner: +x, +y, +z edge (buffer.rs:299-371)
+    for (uint32_t m = mx | my | mz; m; m &= m - 1u) {
+        const uint32_t b = (uint32_t)__ffs((int)m) - 1u, cell = cell0 + b;
+        if ((mx >> b) & 1u) { if (slot < ls.quad_cap) ls.quad_of[slot] = cell; ++slot; }
+        if ((my >> b) & 1u) { if (slot < ls.quad_cap) ls.quad_of[slot] = cell | (1u << 30); ++slot; }
+        if ((mz >> b) & 1u) { if (slot < ls.quad_cap) ls.quad_of[slot] = cell | (2u << 30); ++slot; }
     }
 }
 
@@ -552,8 +547,8 @@ apply_prefix_kernel(Masks m, const uint2* __restrict__ chunk_counts, const uint2
 template <bool kFast, int kVariant>
 __global__ void __launch_bounds__(kThreads, 4)
 vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __restrict__ grids, size_t grid_stride,
-              uint32_t R, uint32_t lg, const uint32_t* __restrict__ cell_of, uint32_t cell_cap, MeshState* st,
-              uint32_t span0, float* __restrict__ out_v, unsigned long long vcap) {
+              uint32_t R, uint32_t lg, const uint32_t* __restrict__ cell_of, uint32_t cell_cap, uint8_t* __restrict__ neg8,
+              MeshState* st, uint32_t span0, float* __restrict__ out_v, unsigned long long vcap) {
     using M = MathExact;
     const uint32_t nv = min(st->group_v, cell_cap);
     const unsigned long long base_v = st->group_base_v;
@@ -571,6 +566,9 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
         float dist[8];
         dist[0] = p[0]; dist[1] = p[1]; dist[2] = p[sy]; dist[3] = p[sy + 1];
         dist[4] = p[sx]; dist[5] = p[sx + 1]; dist[6] = p[sx + sy]; dist[7] = p[sx + sy + 1];
+        // winding of the quads this cell owns uses `dists[(x,y,z)] < 0.0`, not the sign bit (buffer.rs:310:
+        // -0.0 and NaN differ); E4 picks it up by vertex slot instead of re-reading the grid
+        neg8[v] = dist[0] < 0.0f ? 1 : 0;
 
         // p0 = span.start + (x,y,z) * step  (buffer.rs:150-151)
         const float p0x = M::add(g.s[0], M::mul((float)x, g.step[0]));
@@ -692,8 +690,9 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
 // ---------------------------------------------------------------------------
 // E4: quads.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t vertex_id(const uint32_t* __restrict__ active, const uint32_t* __restrict__ word_vpre,
-                                              size_t span_w0, uint32_t c) {
+// group-local vertex slot of active cell c of a span (rank query on the `active` masks)
+__device__ __forceinline__ uint32_t vertex_slot(const uint32_t* __restrict__ active, const uint32_t* __restrict__ word_vpre,
+                                                size_t span_w0, uint32_t c) {
     const size_t o = span_w0 + (c >> 5);
     return word_vpre[o] + __popc(active[o] & ((1u << (c & 31u)) - 1u));
 }
@@ -717,50 +716,32 @@ __device__ __forceinline__ void store_quad(uint32_t* __restrict__ out_idx, unsig
     else      { d[0] = make_uint2(v0, v1); d[1] = make_uint2(v2, v1); d[2] = make_uint2(v3, v2); }   // [v0,v1,v2, v1,v3,v2]
 }
 
-// One thread per ACTIVE cell (the compacted list E2b wrote, cube(R) order): a lower corner can only
-// own a sign-changing edge if its cell is active, and there is about one quad per active cell, so
-// the list is a balanced, coalesced work list for the quads as well.  Persistent grid-stride loop
-// (the list length lives on the device).
+// One thread per QUAD (the list E1+E2 wrote, already in the reference's emission order): every lane has
+// exactly one record to produce, consecutive lanes write consecutive 24-byte records.  The quad of the
+// sign-changing edge from corner c along +x / +y / +z joins the vertices of the four cells around that edge
+// (buffer.rs:302-371): c - a - b, c - a, c - b, c with (a, b) = (R, 1), (R^2, 1), (R^2, R).  Persistent
+// grid-stride loop (the list length lives on the device).
 template <bool kPacked>
 __global__ void __launch_bounds__(kThreads)
-quad_kernel(Masks m, const uint32_t* __restrict__ word_vpre, const uint32_t* __restrict__ word_qpre,
-            const float* __restrict__ grids, size_t grid_stride,
-            uint32_t R, uint32_t lg, uint32_t words_per_span, const uint32_t* __restrict__ cell_of, uint32_t cell_cap,
+quad_kernel(ExtractionLists ls, uint32_t R, uint32_t lg, uint32_t words_per_span,
             MeshState* st, uint32_t* __restrict__ out_idx, unsigned long long icap) {
-    const uint32_t nv = min(st->group_v, cell_cap);
+    const uint32_t nq = min(st->group_q, ls.quad_cap);
     const unsigned long long base_q = st->group_base_q;
-    const uint32_t n = R + 1u, R2 = R << lg, lg3 = 3 * lg;
-    for (uint32_t v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
-        const uint32_t cell = cell_of[v];
+    const uint32_t R2 = R << lg, lg3 = 3 * lg;
+    for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < nq; q += gridDim.x * kThreads) {
+        const uint32_t rec = ls.quad_of[q];
+        const uint32_t edge = rec >> 30, cell = rec & 0x3fffffffu;
         const uint32_t span = cell >> lg3, c = cell & ((1u << lg3) - 1u);
-        const uint32_t b = c & 31u;
         const size_t w0 = (size_t)span * words_per_span;
-        const size_t o = w0 + (c >> 5);
-        const uint32_t bx = m.ex[o], by = m.ey[o], bz = m.ez[o];
-        const uint32_t hx = (bx >> b) & 1u, hy = (by >> b) & 1u, hz = (bz >> b) & 1u;
-        if ((hx | hy | hz) == 0u) continue;
-        const uint32_t lt = (1u << b) - 1u;
-        // quads before this corner: whole words (prefix) + lower corners of this word, in corner order
-        unsigned long long q = base_q + word_qpre[o] + __popc(bx & lt) + __popc(by & lt) + __popc(bz & lt);
-        const uint32_t x = c >> (2 * lg), y = (c >> lg) & (R - 1u), z = c & (R - 1u);
-        // winding uses `dists[(x,y,z)] < 0.0`, not the sign bit (buffer.rs:310): -0.0 and NaN differ
-        const bool neg = grids[(size_t)span * grid_stride + ((size_t)x * n + y) * n + z] < 0.0f;
-        const uint32_t v3 = word_vpre[o] + __popc(m.active[o] & lt);
-        if (hx) {   // +x edge, buffer.rs:302-323
-            store_quad<kPacked>(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R - 1u),
-                                vertex_id(m.active, word_vpre, w0, c - R), vertex_id(m.active, word_vpre, w0, c - 1u), v3,
-                                &st->wire_overflow);
-        }
-        if (hy) {   // +y edge, buffer.rs:326-347 (winding flipped relative to x/z)
-            store_quad<kPacked>(out_idx, q++, icap, !neg, vertex_id(m.active, word_vpre, w0, c - R2 - 1u),
-                                vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - 1u), v3,
-                                &st->wire_overflow);
-        }
-        if (hz) {   // +z edge, buffer.rs:350-371
-            store_quad<kPacked>(out_idx, q++, icap, neg, vertex_id(m.active, word_vpre, w0, c - R2 - R),
-                                vertex_id(m.active, word_vpre, w0, c - R2), vertex_id(m.active, word_vpre, w0, c - R), v3,
-                                &st->wire_overflow);
-        }
+        const uint32_t first = ls.span_first[span];
+        const uint32_t a = edge == 0u ? R : R2, b = edge == 2u ? R : 1u;
+        const uint32_t s3 = vertex_slot(ls.active, ls.word_vpre, w0, c);
+        const uint32_t v0 = vertex_slot(ls.active, ls.word_vpre, w0, c - a - b) - first;
+        const uint32_t v1 = vertex_slot(ls.active, ls.word_vpre, w0, c - a) - first;
+        const uint32_t v2 = vertex_slot(ls.active, ls.word_vpre, w0, c - b) - first;
+        const bool neg = s3 < ls.cell_cap && ls.neg8[s3] != 0;
+        // the +y edge's winding is flipped relative to x / z (buffer.rs:326-347)
+        store_quad<kPacked>(out_idx, base_q + q, icap, edge == 1u ? !neg : neg, v0, v1, v2, s3 - first, &st->wire_overflow);
     }
 }
 

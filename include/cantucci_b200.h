@@ -124,7 +124,7 @@ CTC_API int ctc_ctx_set_overlap(ctc_ctx *ctx, int enable);
  * the three pass timers are always on).  ctc_mesh_kernel_times then returns, for the last call whose
  * result was fetched, the device milliseconds per kernel summed over the launch groups (index CTC_K_*).
  * Meaningful per kernel only with ctc_ctx_set_overlap(0); with overlap on they share the SMs. */
-enum { CTC_K_SAMPLE_GRIDS = 0, CTC_K_FIXUP = 1, CTC_K_CLASSIFY = 2, CTC_K_SCAN = 3, CTC_K_PREFIX = 4,
+enum { CTC_K_SAMPLE_GRIDS = 0, CTC_K_FIXUP = 1, CTC_K_CLASSIFY = 2, CTC_K_SCAN = 3, CTC_K_PREFIX = 4 /* emit_lists */,
        CTC_K_VERTEX = 5, CTC_K_QUADS = 6, CTC_NUM_KERNELS = 8 };
 CTC_API int ctc_ctx_set_kernel_timing(ctc_ctx *ctx, int enable);
 CTC_API int ctc_mesh_kernel_times(ctc_ctx *ctx, double *ms, size_t n);

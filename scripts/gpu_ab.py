@@ -14,7 +14,7 @@ sh = cb.Mandelbulb.classic(6, 2.5, fast=True)._ctc_shape()
 m = DeviceMesher(ctx, torch, dev, 14_000_000, 84_000_000, len(spans))
 res = {}
 for overlap in (False, True):
-    ctx.set_overlap(overlap)
+    ctx.set_overlap(overlap); ctx.set_kernel_timing(not overlap)
     for _ in range(3):
         m.launch(sh, spans, 64); m.result()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -23,10 +23,12 @@ for overlap in (False, True):
     for _ in range(10):
         a.record(); m.launch(sh, spans, 64); nv, ni, t = m.result(); b.record(); torch.cuda.synchronize()
         ts.append((a.elapsed_time(b), t.first_ms, t.second_ms, t.third_ms))
+    if not overlap:
+        km = {k: round(v, 3) for k, v in ctx.kernel_times().items() if v}
     ts = np.array(ts)
     res[overlap] = ts.mean(axis=0)
-print("%%-28s serial: step %%.3f  K1 %%.3f  pass2 %%.3f  pass3 %%.3f | overlapped step %%.3f  (nv %%d, fixups %%s)" %% (
-    os.path.basename(os.environ.get("CANTUCCI_B200_LIB", "default")), *res[False], res[True][0], nv, ctx.mesh_fixups()))
+print("%%-28s serial: step %%.3f  K1 %%.3f  pass2 %%.3f  pass3 %%.3f | overlapped step %%.3f  (nv %%d, fixups %%s) %%s" %% (
+    os.path.basename(os.environ.get("CANTUCCI_B200_LIB", "default")), *res[False], res[True][0], nv, ctx.mesh_fixups(), km))
 ''' % ROOT
 libs = sys.argv[1:] or sorted(glob.glob(os.path.join(ROOT, "build", "ab", "lib_*.so")))
 for lib in libs:
