@@ -575,15 +575,20 @@ def ours_main(args):
             for _ in range(3):
                 e2e_step()
             torch.cuda.synchronize()
+            wire0 = ctx.host_index_wire_stats()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 e2e_step()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / args.steps
+            wire1 = ctx.host_index_wire_stats()
+            packed_wire = wire1[0] - wire0[0] == args.steps and wire1[1] == wire0[1]
             nv, ni = int(v_off[nspans]), int(i_off[nspans])
             e2e = {"value": total_samples / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(nspans * 48),
-                   "d2h_bytes_per_step": int(nv * 28 + ni * 4 + 2 * (nspans + 1) * 8 + 48),
-                   "api": "ctc_mesh_spans (host pointers; pinned host buffers)", "steps": args.steps}
+                   "d2h_bytes_per_step": int(nv * 28 + (ni // 6 * 8 if packed_wire else ni * 4) + 2 * (nspans + 1) * 8 + 48),
+                   "api": "ctc_mesh_spans (host pointers; pinned host buffers)", "steps": args.steps,
+                   "index_wire": (f"packed 8-byte quad records over PCIe, widened into the caller's u32 index buffer by {wire1[2]} host threads "
+                                  "inside the call (the caller receives six u32 per quad)") if packed_wire else "six u32 per quad"}
             # ---- parity gate + CPU baseline: ONE oracle run over the whole volume serves both -----------------
             if not args.no_cpu:
                 ora = oracle_volume(spans)

@@ -70,7 +70,7 @@ EXPORTS = (
     "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
     "ctc_ctx_set_fast_band", "ctc_mesh_fixups", "ctc_fast_sign_probe", "ctc_sample_signs",
     "ctc_ctx_set_kernel_timing", "ctc_mesh_kernel_times", "ctc_iteration_stats_points",
-    "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats",
+    "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats", "ctc_ctx_set_host_index_wire", "ctc_ctx_host_index_wire_stats",
     "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
     "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
 )
@@ -163,6 +163,10 @@ def lib() -> C.CDLL:
     L.ctc_fast_sign_probe.argtypes = [vp, shp, spn, sz, u32, u64p, sz]
     L.ctc_ctx_set_coalescing.restype = C.c_int
     L.ctc_ctx_set_coalescing.argtypes = [vp, C.c_int]
+    L.ctc_ctx_set_host_index_wire.restype = C.c_int
+    L.ctc_ctx_set_host_index_wire.argtypes = [vp, C.c_int]
+    L.ctc_ctx_host_index_wire_stats.restype = C.c_int
+    L.ctc_ctx_host_index_wire_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     L.ctc_ctx_coalescing_stats.restype = C.c_int
     L.ctc_ctx_coalescing_stats.argtypes = [vp, u64p, u64p]
     L.ctc_ctx_set_kernel_timing.restype = C.c_int
@@ -225,6 +229,17 @@ class Context:
 
     def set_overlap(self, enable: bool):
         self.check(lib().ctc_ctx_set_overlap(self._h, 1 if enable else 0))
+
+    def set_host_index_wire(self, mode):
+        """Host destinations of ctc_mesh_spans: packed quad records over PCIe, widened by host threads.
+        0 / False: off; 1 / True (default): calls of >= 128 spans; 2: every call."""
+        self.check(lib().ctc_ctx_set_host_index_wire(self._h, int(mode)))
+
+    def host_index_wire_stats(self):
+        """(calls that used the packed wire, calls that fell back to u32 indices, widening threads)."""
+        a, b, n = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        self.check(lib().ctc_ctx_host_index_wire_stats(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return int(a.value), int(b.value), int(n.value)
 
     def synchronize(self):
         self.check(lib().ctc_ctx_synchronize(self._h))

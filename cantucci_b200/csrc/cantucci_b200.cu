@@ -7,8 +7,12 @@
 #include "../../include/cantucci_b200.h"
 #include "kernels.cuh"
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -56,6 +60,157 @@ struct EventPair { cudaEvent_t a, b; int pass; };
 // below 2^-22.  2^-17 re-evaluates 0.46 % of the samples.
 constexpr float kDefaultKappa = 1.0f / 131072.0f;   // 2^-17
 
+// Widens packed 8-byte quad records (kernels.cuh, store_quad) into the reference's six u32 indices on HOST
+// threads.  ctc_mesh_spans ships the records over PCIe (a third of the index bytes) and a small pool of
+// workers widens each launch group's slice into the caller's index buffer as soon as its copy has landed,
+// while the following groups are still computing / copying.  Every worker takes the same share of every task.
+// kind 0: widen n quad records src -> 6 n u32 at dst;  kind 1: copy `bytes` bytes src -> dst in n 16-byte units
+struct ExpandTask { cudaEvent_t ready; const void* src; void* dst; size_t n; int kind; size_t bytes; };
+
+void expand_quads_scalar(const uint2* __restrict__ rec, size_t n, uint32_t* __restrict__ out) {
+    for (size_t q = 0; q < n; ++q) {
+        const uint2 r = rec[q];
+        const uint32_t a = r.x & 0xFFFFu, b = r.x >> 16, v2 = r.y & 0xFFFFu, v3 = r.y >> 16;
+        const bool flip = a > b;
+        const uint32_t v0 = flip ? b : a, v1 = flip ? a : b;
+        uint32_t* d = out + 6 * q;
+        if (flip) { d[0] = v0; d[1] = v2; d[2] = v1; d[3] = v1; d[4] = v2; d[5] = v3; }     // [v0,v2,v1, v1,v2,v3]
+        else      { d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v1; d[4] = v3; d[5] = v2; }     // [v0,v1,v2, v1,v3,v2]
+    }
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+// Four quads per step: zero-extend the four ids of each, order the first two, and let one cross-lane permute
+// per quad place its six indices where they fall in the 96-byte group (the permute pattern is the winding);
+// three blends assemble three aligned 32-byte lines, written with NON-TEMPORAL stores: the index buffer is
+// write-only here, and a cached store would first read every line from a memory system the device->host
+// copies of the vertices are saturating at the same time.
+__attribute__((target("avx2"))) static inline __m256i quad_ids(const uint2* rec, __m256i* flip) {
+    const __m128i w = _mm_cvtepu16_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i*>(rec)));   // a b v2 v3
+    const __m128i sw = _mm_shuffle_epi32(w, 0xE1);                                                    // b a v2 v3
+    const __m128i v = _mm_blend_epi32(_mm_min_epu32(w, sw), _mm_max_epu32(w, sw), 0x2);               // v0 v1 v2 v3
+    *flip = _mm256_broadcastd_epi32(_mm_cmpgt_epi32(w, sw));                                          // a > b
+    return _mm256_castsi128_si256(v);
+}
+__attribute__((target("avx2"))) void expand_quads_avx2(const uint2* __restrict__ rec, size_t n, uint32_t* __restrict__ out) {
+    // keep = [v0,v1,v2, v1,v3,v2], flip = [v0,v2,v1, v1,v2,v3], rotated to the record's place in the group of four
+    const __m256i k0 = _mm256_setr_epi32(0, 1, 2, 1, 3, 2, 0, 0), f0 = _mm256_setr_epi32(0, 2, 1, 1, 2, 3, 0, 0);   // q0: lanes 0..5
+    const __m256i k1 = _mm256_setr_epi32(2, 1, 3, 2, 0, 0, 0, 1), f1 = _mm256_setr_epi32(1, 1, 2, 3, 0, 0, 0, 2);   // q1: [2..5] -> 0..3, [0..1] -> 6..7
+    const __m256i k2 = _mm256_setr_epi32(3, 2, 0, 0, 0, 1, 2, 1), f2 = _mm256_setr_epi32(2, 3, 0, 0, 0, 2, 1, 1);   // q2: [4..5] -> 0..1, [0..3] -> 4..7
+    const __m256i k3 = _mm256_setr_epi32(0, 0, 0, 1, 2, 1, 3, 2), f3 = _mm256_setr_epi32(0, 0, 0, 2, 1, 1, 2, 3);   // q3: [0..5] -> 2..7
+    size_t q = 0;
+    while (q < n && (reinterpret_cast<uintptr_t>(out + 6 * q) & 31u)) {
+        if (q == 4) { expand_quads_scalar(rec + q, n - q, out + 6 * q); return; }     // destination never 32-byte aligned
+        expand_quads_scalar(rec + q, 1, out + 6 * q); ++q;
+    }
+    for (; q + 4 <= n; q += 4) {
+        __m256i fl0, fl1, fl2, fl3;
+        const __m256i v0 = quad_ids(rec + q, &fl0), v1 = quad_ids(rec + q + 1, &fl1), v2 = quad_ids(rec + q + 2, &fl2), v3 = quad_ids(rec + q + 3, &fl3);
+        const __m256i a = _mm256_permutevar8x32_epi32(v0, _mm256_blendv_epi8(k0, f0, fl0));
+        const __m256i b = _mm256_permutevar8x32_epi32(v1, _mm256_blendv_epi8(k1, f1, fl1));
+        const __m256i c = _mm256_permutevar8x32_epi32(v2, _mm256_blendv_epi8(k2, f2, fl2));
+        const __m256i d = _mm256_permutevar8x32_epi32(v3, _mm256_blendv_epi8(k3, f3, fl3));
+        __m256i* o = reinterpret_cast<__m256i*>(out + 6 * q);
+        _mm256_stream_si256(o, _mm256_blend_epi32(a, b, 0xC0));
+        _mm256_stream_si256(o + 1, _mm256_blend_epi32(b, c, 0xF0));
+        _mm256_stream_si256(o + 2, _mm256_blend_epi32(c, d, 0xFC));
+    }
+    _mm_sfence();
+    expand_quads_scalar(rec + q, n - q, out + 6 * q);
+}
+#endif
+
+void expand_quads_host(const uint2* rec, size_t n, uint32_t* out) {
+    static const bool skip = getenv("CANTUCCI_B200_EXPAND_SKIP") != nullptr;     // measurement aid: copy-only timing
+    if (skip) return;
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) { expand_quads_avx2(rec, n, out); return; }
+#endif
+    expand_quads_scalar(rec, n, out);
+}
+
+// Worker pool: the caller pushes one task per launch group (records landed in the pinned wire buffer once
+// `ready` has fired); workers claim 32 Ki-quad pieces of the tasks in order.
+class HostExpander {
+public:
+    static constexpr size_t kPiece = 32768;
+    ~HostExpander() { stop(); }
+    bool start(int device) {
+        if (!th_.empty()) return true;
+        const unsigned hw = std::thread::hardware_concurrency();
+        int n = hw >= 8 ? (int)hw / 2 : (hw >= 2 ? (int)hw - 1 : 1);
+        if (const char* e = getenv("CANTUCCI_B200_EXPAND_THREADS")) { const int v = atoi(e); if (v >= 1) n = v; }
+        if (n > 32) n = 32;
+        try {
+            for (int k = 0; k < n; ++k) th_.emplace_back([this, device] { run(device); });
+        } catch (...) { stop(); return false; }
+        return true;
+    }
+    void begin() {
+        std::lock_guard<std::mutex> lk(mu_);
+        tasks_.clear(); closed_ = false; cur_ = 0; piece_ = 0; waited_ = 0; busy_ = 0;
+    }
+    void push(const ExpandTask& t) {
+        std::lock_guard<std::mutex> lk(mu_);
+        tasks_.push_back(t);
+        cv_.notify_all();
+    }
+    void finish() {       // no more tasks for this call; returns when every piece has been widened
+        std::unique_lock<std::mutex> lk(mu_);
+        closed_ = true;
+        cv_.notify_all();
+        done_.wait(lk, [&] { return cur_ >= tasks_.size() && busy_ == 0; });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu_); quit_ = true; cv_.notify_all(); }
+        for (std::thread& t : th_) if (t.joinable()) t.join();
+        th_.clear();
+        quit_ = false;
+    }
+    size_t threads() const { return th_.size(); }
+private:
+    void run(int device) {
+        cudaSetDevice(device);
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return quit_ || cur_ < tasks_.size(); });
+            if (quit_) return;
+            const size_t ti = cur_;
+            const ExpandTask t = tasks_[ti];
+            if (waited_ <= ti) {              // the task's copy has not been waited for yet: one worker does (blocking event)
+                if (waiting_) { cv_.wait(lk, [&] { return quit_ || !waiting_; }); continue; }
+                waiting_ = true;
+                lk.unlock();
+                cudaEventSynchronize(t.ready);
+                lk.lock();
+                waiting_ = false; waited_ = ti + 1;
+                cv_.notify_all();
+                continue;
+            }
+            const size_t lo = piece_ * kPiece;
+            if (lo >= t.n) { if (cur_ == ti) { ++cur_; piece_ = 0; if (cur_ >= tasks_.size()) done_.notify_all(); } continue; }
+            ++piece_; ++busy_;
+            lk.unlock();
+            const size_t hi = lo + kPiece < t.n ? lo + kPiece : t.n;
+            if (t.kind == 0) {
+                expand_quads_host(static_cast<const uint2*>(t.src) + lo, hi - lo, static_cast<uint32_t*>(t.dst) + 6 * lo);
+            } else {
+                memcpy(static_cast<char*>(t.dst) + 16 * lo, static_cast<const char*>(t.src) + 16 * lo, (16 * hi < t.bytes ? 16 * hi : t.bytes) - 16 * lo);
+            }
+            lk.lock();
+            if (--busy_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::vector<ExpandTask> tasks_;
+    size_t cur_ = 0, piece_ = 0, waited_ = 0;
+    int busy_ = 0;
+    bool closed_ = false, quit_ = false, waiting_ = false;
+};
+
 }  // namespace
 
 struct MeshRequest;
@@ -86,6 +241,14 @@ struct ctc_ctx {
     double kernel_ms[CTC_NUM_KERNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool overlap = true;        // ctc_ctx_set_overlap
     bool wire_quads = false;    // ctc_ctx_set_index_wire: ctc_mesh_spans delivers packed 8-byte quad records
+    // host destinations: indices cross PCIe as packed quad records and are widened by host threads (default on;
+    // a span with >= 65536 vertices makes the call fall back to u32 indices on the wire)
+    int host_wire = 1;          // ctc_ctx_set_host_index_wire: 0 off, 1 calls of >= 128 spans, 2 every call
+    bool last_wire_overflow = false;
+    uint64_t host_wire_calls = 0, host_wire_fallbacks = 0;
+    HostExpander expander;
+    PinnedBuf h_wire, h_vstage;   // pinned landing buffers: packed quad records; vertices bound for PAGEABLE memory
+    std::vector<cudaEvent_t> wire_events;
     // fast mode's sign-trust band (de_device.cuh, fast_suspect_*); calibrated by ctc_fast_sign_probe
     float kappa = kDefaultKappa;
 
@@ -416,7 +579,7 @@ int ensure_progress(ctc_ctx* ctx, size_t groups) {
 
 int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t R,
                     ctc_vertex* d_v, size_t vcap, uint32_t* d_idx, size_t icap, uint64_t* d_v_off, uint64_t* d_i_off,
-                    bool pipeline = false) {
+                    bool pipeline = false, bool packed_quads = false) {
     ShapeDev sh; uint32_t lg;
     int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
     rc = check_spans(ctx, spans, nspans, R, &lg); if (rc) return rc;
@@ -587,7 +750,7 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         }
         {   // pass 3
             PassTimer t(ctx, 2, sE);
-            if (pipeline && ctx->wire_quads)
+            if (pipeline && packed_quads)
                 quad_kernel<true><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st, d_idx, (unsigned long long)icap);
             else
                 quad_kernel<false><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st, d_idx, (unsigned long long)icap);
@@ -634,6 +797,7 @@ int mesh_result_impl(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ct
     char lerp[160] = "";
     if (st->panic_span != 0xFFFFFFFFu)
         snprintf(lerp, sizeof lerp, "lerp factor outside [0,1] in span %u: the reference panics at math.rs:19", st->panic_span);
+    ctx->last_wire_overflow = st->wire_overflow != 0;
     if (st->wire_overflow)
         return fail(ctx, CTC_ERR_OVERFLOW, "a span has >= 65536 vertices: packed quad records cannot carry it, use the u32 index wire");
     if (st->overflow)
@@ -685,7 +849,9 @@ void ctc_ctx_destroy(ctc_ctx* c) {
                       &c->span_first, &c->neg8, &c->chunk_cnt, &c->span_tot, &c->span_pre, &c->state, &c->out_v, &c->out_idx,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
-    c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release();
+    c->expander.stop();
+    c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release(); c->h_wire.release(); c->h_vstage.release();
+    for (cudaEvent_t e : c->wire_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->k1_done) cudaEventDestroy(e);
@@ -739,6 +905,22 @@ int ctc_ctx_set_index_wire(ctc_ctx* ctx, int packed_quads) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->wire_quads = packed_quads != 0;
+    return CTC_OK;
+}
+
+int ctc_ctx_set_host_index_wire(ctc_ctx* ctx, int packed_quads) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->host_wire = packed_quads < 0 ? 0 : (packed_quads > 2 ? 2 : packed_quads);
+    return CTC_OK;
+}
+
+int ctc_ctx_host_index_wire_stats(ctc_ctx* ctx, uint64_t* calls, uint64_t* fallbacks, uint32_t* threads) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (calls) *calls = ctx->host_wire_calls;
+    if (fallbacks) *fallbacks = ctx->host_wire_fallbacks;
+    if (threads) *threads = (uint32_t)ctx->expander.threads();
     return CTC_OK;
 }
 
@@ -851,20 +1033,35 @@ int ctc_mesh_result(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc
     return guarded(ctx, [&] { return mesh_result_impl(ctx, n_vertices, n_indices, timings); });
 }
 
-static int mesh_spans_host(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
-                           ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
-                           ctc_timings* timings) {
-    if (!v_off || !i_off) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "offset tables are NULL");
-    if ((vcap && !v) || (icap && !idx)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL output buffer with non-zero capacity");
+static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                                ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
+                                ctc_timings* timings, bool host_wire) {
     CK(cudaSetDevice(ctx->device));
     CK(ctx->out_v.ensure((vcap ? vcap : 1) * sizeof(ctc_vertex)));
     CK(ctx->out_idx.ensure((icap ? icap : 1) * sizeof(uint32_t)));
     CK(ctx->off_v.ensure((nspans + 1) * 8)); CK(ctx->off_i.ensure((nspans + 1) * 8));
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->copy_stream2) CK(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+    // Buffers in PAGEABLE host memory (what the reference's caller owns: a Vec) are filled through pinned landing
+    // buffers at full PCIe rate, and host threads copy them on, instead of the driver's single staged pageable copy
+    // (calls of a few spans keep the direct copy: less than a megabyte is not worth a hand-over between threads).
+    auto pageable = [](const void* p) {
+        cudaPointerAttributes a{};
+        const bool un = cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeUnregistered;
+        (void)cudaGetLastError();
+        return un;
+    };
+    bool stage_v = nspans > 8 && v && vcap && pageable(v);
+    bool stage_i = nspans > 8 && !host_wire && !ctx->wire_quads && idx && icap && pageable(idx);
+    if ((host_wire || stage_v || stage_i) && !ctx->expander.start(ctx->device)) host_wire = stage_v = stage_i = false;
+    if (host_wire) CK(ctx->h_wire.ensure((icap / 6 + 1) * sizeof(uint2)));
+    if (stage_i && ctx->h_wire.ensure(icap * sizeof(uint32_t)) != cudaSuccess) { (void)cudaGetLastError(); stage_i = false; }
+    if (stage_v && ctx->h_vstage.ensure(vcap * sizeof(ctc_vertex)) != cudaSuccess) { (void)cudaGetLastError(); stage_v = false; }
+    const bool packed = ctx->wire_quads || host_wire;
+    const bool workers = host_wire || stage_v || stage_i;
     int rc = mesh_spans_impl(ctx, shape, spans, nspans, resolution, ctx->out_v.as<ctc_vertex>(), vcap,
                              ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
-                             /*pipeline=*/true);
+                             /*pipeline=*/true, packed);
     if (rc) return rc;
     // Everything is enqueued.  The offset tables follow the kernels on the compute stream (straight
     // to the destination when it is device/peer memory, through a pinned staging buffer when it is
@@ -886,28 +1083,61 @@ static int mesh_spans_host(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span*
     }
     CK(ctx->h_state.ensure(sizeof(MeshState)));
     CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (workers) {
+        while (ctx->wire_events.size() < 2 * ctx->n_groups) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->wire_events.push_back(e);
+        }
+        ctx->expander.begin();
+        if (host_wire) ctx->host_wire_calls++;
+    }
     size_t done_v = 0, done_i = 0;
-    for (size_t g = 0; g < ctx->n_groups; ++g) {
-        CK(cudaEventSynchronize(ctx->group_events[g]));
+    int copy_rc = CTC_OK;
+    for (size_t g = 0; g < ctx->n_groups && copy_rc == CTC_OK; ++g) {
+        cudaError_t e = cudaEventSynchronize(ctx->group_events[g]);
         const unsigned long long tv = ctx->progress_h[2 * g], ti = 6ull * ctx->progress_h[2 * g + 1];
         const size_t cv = tv < vcap ? (size_t)tv : vcap, ci = ti < icap ? (size_t)ti : icap;
-        if (cv > done_v) {
-            CK(cudaMemcpyAsync(v + done_v, ctx->out_v.as<ctc_vertex>() + done_v, (cv - done_v) * sizeof(ctc_vertex),
-                               cudaMemcpyDefault, ctx->copy_stream));
+        if (e == cudaSuccess && cv > done_v) {
+            if (stage_v) {
+                ctc_vertex* hv = static_cast<ctc_vertex*>(ctx->h_vstage.p);
+                const size_t bytes = (cv - done_v) * sizeof(ctc_vertex);
+                e = cudaMemcpyAsync(hv + done_v, ctx->out_v.as<ctc_vertex>() + done_v, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+                cudaEvent_t ev = ctx->wire_events[ctx->n_groups + g];
+                if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->copy_stream);
+                if (e == cudaSuccess) ctx->expander.push(ExpandTask{ev, hv + done_v, v + done_v, (bytes + 15) / 16, 1, bytes});
+            } else {
+                e = cudaMemcpyAsync(v + done_v, ctx->out_v.as<ctc_vertex>() + done_v, (cv - done_v) * sizeof(ctc_vertex),
+                                    cudaMemcpyDefault, ctx->copy_stream);
+            }
             done_v = cv;
         }
-        if (ci > done_i) {
-            if (ctx->wire_quads) {      // packed records: 8 bytes per quad (= per 6 indices), densely at quad offsets
-                const size_t q0 = done_i / 6, q1 = ci / 6;
-                CK(cudaMemcpyAsync(reinterpret_cast<uint2*>(idx) + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2),
-                                   cudaMemcpyDefault, ctx->copy_stream2));
+        if (e == cudaSuccess && ci > done_i) {
+            const size_t q0 = done_i / 6, q1 = ci / 6;
+            if (host_wire) {            // packed records to the pinned wire buffer; host threads widen them into idx
+                uint2* hw = static_cast<uint2*>(ctx->h_wire.p);
+                e = cudaMemcpyAsync(hw + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->copy_stream2);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->wire_events[g], ctx->copy_stream2);
+                if (e == cudaSuccess) ctx->expander.push(ExpandTask{ctx->wire_events[g], hw + q0, idx + 6 * q0, q1 - q0, 0, 0});
+            } else if (stage_i) {
+                uint32_t* hi = static_cast<uint32_t*>(ctx->h_wire.p);
+                const size_t bytes = (ci - done_i) * sizeof(uint32_t);
+                e = cudaMemcpyAsync(hi + done_i, ctx->out_idx.as<uint32_t>() + done_i, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream2);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->wire_events[g], ctx->copy_stream2);
+                if (e == cudaSuccess) ctx->expander.push(ExpandTask{ctx->wire_events[g], hi + done_i, idx + done_i, (bytes + 15) / 16, 1, bytes});
+            } else if (ctx->wire_quads) {      // packed records: 8 bytes per quad (= per 6 indices), densely at quad offsets
+                e = cudaMemcpyAsync(reinterpret_cast<uint2*>(idx) + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2),
+                                    cudaMemcpyDefault, ctx->copy_stream2);
             } else {
-                CK(cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
-                                   cudaMemcpyDefault, ctx->copy_stream2));
+                e = cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
+                                    cudaMemcpyDefault, ctx->copy_stream2);
             }
             done_i = ci;
         }
+        if (e != cudaSuccess) copy_rc = fail_cuda(ctx, e, "pipelined device->host copy");
     }
+    if (workers) ctx->expander.finish();         // (always: the workers must be idle before the landing buffers are reused)
+    if (copy_rc != CTC_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return copy_rc; }
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream2));
     uint64_t nv = 0, ni = 0;
@@ -917,6 +1147,29 @@ static int mesh_spans_host(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span*
         memcpy(i_off, static_cast<char*>(ctx->h_tables.p) + tbytes, tbytes);
     }
     return status;
+}
+
+static int mesh_spans_host(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                           ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
+                           ctc_timings* timings) {
+    if (!v_off || !i_off) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "offset tables are NULL");
+    if ((vcap && !v) || (icap && !idx)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL output buffer with non-zero capacity");
+    // Index wire for HOST destinations: packed 8-byte quad records over PCIe, widened by host threads.
+    // (calls of fewer than 128 spans are not PCIe-bound: they keep six u32 per quad on the wire)
+    bool host_wire = ctx->host_wire && !ctx->wire_quads && idx != nullptr && icap >= 6 && (nspans >= 128 || ctx->host_wire == 2);
+    if (host_wire) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, idx) == cudaSuccess && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged))
+            host_wire = false;
+        (void)cudaGetLastError();
+    }
+    int rc = mesh_spans_host_once(ctx, shape, spans, nspans, resolution, v, vcap, idx, icap, v_off, i_off, timings, host_wire);
+    if (host_wire && rc == CTC_ERR_OVERFLOW && ctx->last_wire_overflow) {
+        // a span with >= 65536 vertices does not fit the 16-bit records: once more with u32 indices on the wire
+        ctx->host_wire_fallbacks++;
+        rc = mesh_spans_host_once(ctx, shape, spans, nspans, resolution, v, vcap, idx, icap, v_off, i_off, timings, false);
+    }
+    return rc;
 }
 
 }  // extern "C" (reopened below)

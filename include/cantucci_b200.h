@@ -264,6 +264,16 @@ CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
  * on the context's stream). */
 CTC_API int ctc_ctx_set_index_wire(ctc_ctx *ctx, int packed_quads);
 CTC_API int ctc_expand_quads(ctc_ctx *ctx, const void *d_records, size_t nquads, uint32_t *d_idx);
+/* HOST destinations of ctc_mesh_spans (what the reference's caller passes, mesh/mod.rs:141-148): by default
+ * (1) the indices cross PCIe as the packed 8-byte records above and a pool of host threads widens every launch
+ * group's slice into the caller's u32 index buffer while later groups are still computing -- the caller sees
+ * exactly the reference's six u32 per quad, the device->host copy carries a third of the index bytes.  A span
+ * with >= 65536 vertices makes the call repeat itself with u32 indices on the wire (counted in `fallbacks`).
+ * Calls of fewer than 128 spans are not PCIe-bound and keep six u32 per quad (2: packed records for every call).
+ * 0: always copy six u32 per quad.  Independently of this switch, buffers in PAGEABLE host memory are filled
+ * through pinned landing buffers by the same host threads (calls of more than 8 spans). */
+CTC_API int ctc_ctx_set_host_index_wire(ctc_ctx *ctx, int packed_quads);
+CTC_API int ctc_ctx_host_index_wire_stats(ctc_ctx *ctx, uint64_t *calls, uint64_t *fallbacks, uint32_t *threads);
 
 /* Page-lock / unlock host memory the caller owns (cudaHostRegister, portable), e.g. a POSIX shared-
  * memory segment that several one-GPU processes fill with ctc_mesh_spans, each over its own PCIe link. */

@@ -338,3 +338,52 @@ def test_dense_512_as_spans_properties(ctx):
     again, _ = cb.generate_for_boxes(tiles, bulb, 64, ctx)
     assert np.array_equal(again.indices, batch.indices)
     assert np.array_equal(again.vertices.view(np.uint32), batch.vertices.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_host_index_wire_delivers_the_same_indices_and_falls_back(oracle, ctx):
+    """Host destinations get their indices as packed quad records over PCIe, widened by host threads
+    (default on): the caller must see exactly the six u32 per quad of the plain copy; a span with >= 65536
+    vertices (a sphere at R = 256) makes the call repeat itself on the u32 wire."""
+    import cantucci_b200 as cb
+    tree = cb.startup_tree(cb.Mandelbulb.classic(6, 2.5).bounding_box())
+    spans = cb.spans_array([n.span for n in tree.leaves()])
+    shape = cb.Mandelbulb.classic(6, 2.5)
+    calls0, fb0, threads = ctx.host_index_wire_stats()
+    auto, _ = cb.generate_for_boxes(spans, shape, 64, ctx)          # 64 spans: below the automatic threshold
+    assert ctx.host_index_wire_stats()[0] == calls0
+    ctx.set_host_index_wire(2)
+    packed, _ = cb.generate_for_boxes(spans, shape, 64, ctx)
+    calls1, fb1, threads = ctx.host_index_wire_stats()
+    assert calls1 > calls0 and fb1 == fb0 and threads >= 1
+    assert np.array_equal(auto.indices, packed.indices)
+    ctx.set_host_index_wire(False)
+    try:
+        plain, _ = cb.generate_for_boxes(spans, shape, 64, ctx)
+    finally:
+        ctx.set_host_index_wire(True)
+    assert np.array_equal(packed.indices, plain.indices) and np.array_equal(packed.i_off, plain.i_off)
+    assert np.array_equal(packed.vertices.view(np.uint32), plain.vertices.view(np.uint32))
+    # one span with > 65536 vertices: a sphere at R = 256 (about 140 k surface cells)
+    bbox = np.array([[-1.2, -1.2, -1.2, 1.2, 1.2, 1.2]], dtype=np.float32)
+    ctx.set_host_index_wire(2)
+    big, t = cb.generate_for_boxes(bbox, cb.Sphere((0.0, 0.0, 0.0), 1.0), 256, ctx)
+    assert t.vertices >= 65536 and int(big.indices.max()) == t.vertices - 1
+    assert ctx.host_index_wire_stats()[1] == fb1 + 1
+    ctx.set_host_index_wire(False)
+    try:
+        plain_big, _ = cb.generate_for_boxes(bbox, cb.Sphere((0.0, 0.0, 0.0), 1.0), 256, ctx)
+    finally:
+        ctx.set_host_index_wire(True)
+    assert np.array_equal(big.indices, plain_big.indices)
+    # the automatic mode on a call large enough for it: the 6^3 tiling of the bounding box
+    tiles = cb.tile_volume(cb.Span((-1.2,) * 3, (1.2,) * 3), 6)
+    calls2 = ctx.host_index_wire_stats()[0]
+    a, _ = cb.generate_for_boxes(tiles, shape, 64, ctx)
+    assert ctx.host_index_wire_stats()[0] == calls2 + 1
+    ctx.set_host_index_wire(False)
+    try:
+        b, _ = cb.generate_for_boxes(tiles, shape, 64, ctx)
+    finally:
+        ctx.set_host_index_wire(True)
+    assert np.array_equal(a.indices, b.indices) and np.array_equal(a.vertices.view(np.uint32), b.vertices.view(np.uint32))
