@@ -416,7 +416,9 @@ def ours_main(args):
     strong = None
     if not args.no_strong and args.tiles == TILES:
         vol5 = workload_spans(64)                          # the 4096^3 volume as 64^3 spans of R = 64: 262 144 spans
-        sched5, local5, info5 = make_scheduler(vol5, "interleave", args.gather, wire_packed_from=5)
+        # (u32 indices on the wire: with 1/N of the volume per rank the gather is far from ingest-bound -- rank 0
+        # takes in 11.9 GB during ~45 ms of compute at N = 8 -- and nothing is left to widen after the last put)
+        sched5, local5, info5 = make_scheduler(vol5, "interleave", args.gather, wire_packed_from=99)
         # (a few of the 262 144 spans carry NaN samples next to the surface: the reference's worker would panic
         # there, math.rs:19, and lose that one job; the C ABI reports CTC_ERR_LERP_ASSERT and still delivers)
         step5 = lambda: run_step(sched5, vol5, local5, allow_lerp_assert=True)

@@ -136,10 +136,11 @@ class HostExpander {
 public:
     static constexpr size_t kPiece = 32768;
     ~HostExpander() { stop(); }
-    bool start(int device) {
+    bool start(int device, int share = 1) {      // share: contexts of this process that run such a pool side by side
         if (!th_.empty()) return true;
         const unsigned hw = std::thread::hardware_concurrency();
         int n = hw >= 8 ? (int)hw / 2 : (hw >= 2 ? (int)hw - 1 : 1);
+        if (share > 1) { n /= share; if (n < 2) n = 2; }
         if (const char* e = getenv("CANTUCCI_B200_EXPAND_THREADS")) { const int v = atoi(e); if (v >= 1) n = v; }
         if (n > 32) n = 32;
         try {
@@ -247,6 +248,12 @@ struct ctc_ctx {
     bool last_wire_overflow = false;
     uint64_t host_wire_calls = 0, host_wire_fallbacks = 0;
     HostExpander expander;
+    // peer destination, packed wire: after every launch group's records a progress word {done:1 | epoch:23 | quads:40}
+    // is put into the destination GPU's memory, so that it can widen the slices that have landed while this GPU is still computing
+    void* wire_progress = nullptr;          // ctc_ctx_set_wire_progress
+    uint64_t wire_epoch = 0;
+    PinnedBuf h_wire_prog;
+    int expander_share = 1;     // ctc_multi: one pool per device, the host threads are shared out
     PinnedBuf h_wire, h_vstage;   // pinned landing buffers: packed quad records; vertices bound for PAGEABLE memory
     std::vector<cudaEvent_t> wire_events;
     // fast mode's sign-trust band (de_device.cuh, fast_suspect_*); calibrated by ctc_fast_sign_probe
@@ -850,7 +857,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
     c->expander.stop();
-    c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release(); c->h_wire.release(); c->h_vstage.release();
+    c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release(); c->h_wire.release(); c->h_vstage.release(); c->h_wire_prog.release();
     for (cudaEvent_t e : c->wire_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
@@ -905,6 +912,15 @@ int ctc_ctx_set_index_wire(ctc_ctx* ctx, int packed_quads) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->wire_quads = packed_quads != 0;
+    return CTC_OK;
+}
+
+int ctc_ctx_set_wire_progress(ctc_ctx* ctx, void* d_progress_word) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (reinterpret_cast<uintptr_t>(d_progress_word) & 7u) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "progress word must be 8-byte aligned");
+    ctx->wire_progress = d_progress_word;
+    ctx->wire_epoch = 0;
     return CTC_OK;
 }
 
@@ -1053,7 +1069,7 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
     };
     bool stage_v = nspans > 8 && v && vcap && pageable(v);
     bool stage_i = nspans > 8 && !host_wire && !ctx->wire_quads && idx && icap && pageable(idx);
-    if ((host_wire || stage_v || stage_i) && !ctx->expander.start(ctx->device)) host_wire = stage_v = stage_i = false;
+    if ((host_wire || stage_v || stage_i) && !ctx->expander.start(ctx->device, ctx->expander_share)) host_wire = stage_v = stage_i = false;
     if (host_wire) CK(ctx->h_wire.ensure((icap / 6 + 1) * sizeof(uint2)));
     if (stage_i && ctx->h_wire.ensure(icap * sizeof(uint32_t)) != cudaSuccess) { (void)cudaGetLastError(); stage_i = false; }
     if (stage_v && ctx->h_vstage.ensure(vcap * sizeof(ctc_vertex)) != cudaSuccess) { (void)cudaGetLastError(); stage_v = false; }
@@ -1092,6 +1108,13 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
         ctx->expander.begin();
         if (host_wire) ctx->host_wire_calls++;
     }
+    unsigned long long* wprog = nullptr;
+    unsigned long long wtag = 0;
+    if (ctx->wire_progress && ctx->wire_quads && !workers) {
+        CK(ctx->h_wire_prog.ensure((ctx->n_groups + 2) * 8));
+        wprog = static_cast<unsigned long long*>(ctx->h_wire_prog.p);
+        wtag = (++ctx->wire_epoch & 0x7FFFFFull) << 40;
+    }
     size_t done_v = 0, done_i = 0;
     int copy_rc = CTC_OK;
     for (size_t g = 0; g < ctx->n_groups && copy_rc == CTC_OK; ++g) {
@@ -1128,6 +1151,10 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
             } else if (ctx->wire_quads) {      // packed records: 8 bytes per quad (= per 6 indices), densely at quad offsets
                 e = cudaMemcpyAsync(reinterpret_cast<uint2*>(idx) + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2),
                                     cudaMemcpyDefault, ctx->copy_stream2);
+                if (wprog && e == cudaSuccess) {       // ... and the word that says how far the records have come
+                    wprog[g] = wtag | (unsigned long long)q1;
+                    e = cudaMemcpyAsync(ctx->wire_progress, wprog + g, 8, cudaMemcpyDefault, ctx->copy_stream2);
+                }
             } else {
                 e = cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
                                     cudaMemcpyDefault, ctx->copy_stream2);
@@ -1135,6 +1162,11 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
             done_i = ci;
         }
         if (e != cudaSuccess) copy_rc = fail_cuda(ctx, e, "pipelined device->host copy");
+    }
+    if (wprog && copy_rc == CTC_OK) {        // the last word: everything of this call is there
+        wprog[ctx->n_groups] = (1ull << 63) | wtag | (unsigned long long)(done_i / 6);
+        if (cudaMemcpyAsync(ctx->wire_progress, wprog + ctx->n_groups, 8, cudaMemcpyDefault, ctx->copy_stream2) != cudaSuccess)
+            copy_rc = fail_cuda(ctx, cudaGetLastError(), "wire progress");
     }
     if (workers) ctx->expander.finish();         // (always: the workers must be idle before the landing buffers are reused)
     if (copy_rc != CTC_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return copy_rc; }

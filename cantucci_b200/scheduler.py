@@ -228,6 +228,7 @@ class PeerGatherScheduler:
         sizes = [int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, 2 * int(self.base_t[-1]) * 8]
         if self.wire_quads:
             sizes.append(int(self.base_i[-1]) // 6 * 8 + 64)      # packed quad records of every rank, at quad offsets
+            sizes.append(world * 8)                               # one progress word per rank (ctc_ctx_set_wire_progress)
         self.ptrs = [C.c_void_p() for _ in sizes]
         handles = [None]
         if rank == 0:
@@ -237,6 +238,9 @@ class PeerGatherScheduler:
                 h = C.create_string_buffer(64)
                 ctx.check(L.ctc_ipc_export(ctx.handle, p, h))
                 hs.append(h.raw)
+            if self.wire_quads:      # the progress words start at zero BEFORE any sender can learn where they are
+                torch.as_tensor(_RawCuda(self.ptrs[4].value, 256), device=device).zero_()
+                torch.cuda.synchronize(device)
             handles = [hs]
         if world > 1:
             dist.broadcast_object_list(handles, src=0)
@@ -244,6 +248,16 @@ class PeerGatherScheduler:
             for p, h in zip(self.ptrs, handles[0]):
                 ctx.check(L.ctc_ipc_open(ctx.handle, h, C.byref(p)))
         self.sizes = sizes
+        # packed wire: senders report how far their records have come, rank 0 widens what has landed while everybody
+        # is still computing (a second context = a second stream for the widening kernels)
+        self._epoch = 0
+        self._ctx2 = self._poll_stream = self._flags = None
+        if self.wire_quads:
+            if rank == 0:
+                self._ctx2 = _lib.Context(ctx.device)
+                self._poll_stream = torch.cuda.Stream(device=device)
+            else:
+                ctx.check(L.ctc_ctx_set_wire_progress(ctx.handle, C.c_void_p(self.ptrs[4].value + 8 * rank)))
         # rank-local scratch for rank 0's own device call (offset tables live in the shared table buffers)
         self._views = None
         if rank == 0:
@@ -251,9 +265,14 @@ class PeerGatherScheduler:
             self._views = (raw[0][: sizes[0]].view(torch.float32).view(-1, 7), raw[1][: sizes[1]].view(torch.int32),
                            raw[2][: sizes[2]].view(torch.int64))
             self._local = np.ascontiguousarray(np.zeros((0, 6), dtype=np.float32))
+            if self.wire_quads:
+                self._flags = raw[4][: world * 8].view(torch.int64)
 
     def close(self):
         L = _lib.lib()
+        if self.wire_quads and self.rank != 0:
+            L.ctc_ctx_set_wire_progress(self.ctx.handle, None)
+        self._ctx2 = self._flags = None
         for p in self.ptrs:
             if p.value:
                 (L.ctc_device_free if self.rank == 0 else L.ctc_ipc_close)(self.ctx.handle, p)
@@ -275,9 +294,12 @@ class PeerGatherScheduler:
         if local is None:
             local = np.ascontiguousarray(spans[self.shards[rank]])
         pv, pi, tv, ti = self._region(rank)
+        self._epoch += 1
         if rank == 0 or self.direct:
             ctx.check(L.ctc_mesh_spans_device(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0],
                                               resolution, pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti))
+            if rank == 0 and self.wire_quads:
+                self._widen_arrivals()          # ... while this rank's own kernels run
             rc = L.ctc_mesh_result(ctx.handle, None, None, None)
         else:
             if self.wire_quads:          # destination: this rank's slot of the wire buffer (8 bytes per quad)
@@ -299,15 +321,37 @@ class PeerGatherScheduler:
         if rank != 0:
             return None
         tables = self._views[2].cpu().numpy()      # one small D2H: every rank's offset tables
-        if self.wire_quads:
-            nt = int(self.base_t[-1])
-            for r in range(1, world):    # widen every rank's packed records into the gathered index buffer
-                nq = int(tables[nt + self.base_t[r + 1] - 1]) // 6
-                src = self.ptrs[3].value + int(self.base_i[r]) // 6 * 8
-                dst = self.ptrs[1].value + int(self.base_i[r]) * 4
-                ctx.check(L.ctc_expand_quads(ctx.handle, src, nq, dst))
-            ctx.synchronize()            # the gathered index buffer is complete when run() returns
         return LazyGather(self, tables)
+
+    def _widen_arrivals(self, timeout_s: float = 60.0):
+        """Rank 0, packed wire: polls the senders' progress words and widens every slice of packed quad records
+        that has landed into the gathered u32 index buffer (second stream), until every sender has reported the
+        end of its call.  The gathered index buffer is complete when this returns."""
+        import time
+        L, torch, world = _lib.lib(), self.torch, self.world
+        c2 = self._ctx2
+        done = [0] * world
+        open_ranks = set(range(1, world))
+        tag = self._epoch & 0x7FFFFF
+        t_end = time.perf_counter() + timeout_s
+        while open_ranks:
+            with torch.cuda.stream(self._poll_stream):
+                words = self._flags.cpu().numpy().view(np.uint64)
+            for r in list(open_ranks):
+                w = int(words[r])
+                if (w >> 40) & 0x7FFFFF != tag:
+                    continue
+                q = w & ((1 << 40) - 1)
+                if q > done[r]:
+                    src = self.ptrs[3].value + (int(self.base_i[r]) // 6 + done[r]) * 8
+                    dst = self.ptrs[1].value + (int(self.base_i[r]) + 6 * done[r]) * 4
+                    c2.check(L.ctc_expand_quads(c2.handle, src, q - done[r], dst))
+                    done[r] = q
+                if w >> 63:
+                    open_ranks.discard(r)
+            if time.perf_counter() > t_end:
+                break                    # a sender failed before its last word: the status agreement below reports it
+        c2.synchronize()
 
 
 class LazyGather:

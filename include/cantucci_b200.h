@@ -264,6 +264,13 @@ CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
  * on the context's stream). */
 CTC_API int ctc_ctx_set_index_wire(ctc_ctx *ctx, int packed_quads);
 CTC_API int ctc_expand_quads(ctc_ctx *ctx, const void *d_records, size_t nquads, uint32_t *d_idx);
+/* Packed index wire towards a PEER GPU (ctc_ctx_set_index_wire(ctx, 1), device destination): after every launch
+ * group's records ctc_mesh_spans also puts one 64-bit progress word {done:1 | call epoch:23 | quads so far:40}
+ * at d_progress_word (memory of the destination GPU), in order behind the records, and a last one with the
+ * done bit when the call's records are all there.  The destination can widen the slices that have landed
+ * (ctc_expand_quads) while the sender is still computing instead of after the step.  The epoch counts the
+ * sender's calls since the word was set (first call = 1).  NULL switches it off. */
+CTC_API int ctc_ctx_set_wire_progress(ctc_ctx *ctx, void *d_progress_word);
 /* HOST destinations of ctc_mesh_spans (what the reference's caller passes, mesh/mod.rs:141-148): by default
  * (1) the indices cross PCIe as the packed 8-byte records above and a pool of host threads widens every launch
  * group's slice into the caller's u32 index buffer while later groups are still computing -- the caller sees
