@@ -699,6 +699,23 @@ def other_configs(ctx, cb, _lib, refine, torch, device, stream, DeviceMesher, no
                                                    "group's extraction); iteration means from 1/16 of the spans, spread evenly through the volume"}
     del m4
     torch.cuda.empty_cache()
+    # DE-bound span culling, on/off pair on the benched volume.  The headline and every figure above
+    # are culling-OFF: skipped work does not count as throughput.
+    t0 = time.perf_counter()
+    keep = cb.cull_spans(tiles, cb.Mandelbulb.classic(MAX_ITERS, BAILOUT), RES, ctx)
+    cull_ms = (time.perf_counter() - t0) * 1e3
+    kept = np.ascontiguousarray(tiles[keep])
+    mc = DeviceMesher(ctx, torch, device, 14_000_000, 84_000_000, len(tiles))
+    ms_off = timed(lambda: (mc.launch(sh, tiles, RES), mc.result()), 10)
+    nv_off = mc.result()[0]
+    ms_on = timed(lambda: (mc.launch(sh, kept, RES), mc.result()), 10)
+    nv_on = mc.result()[0]
+    out["culling_1024cube"] = {"spans": int(len(tiles)), "spans_culled": int((~keep).sum()), "rule": "DE(centre) > 2 x half-diagonal of the skirt-expanded span",
+                               "cull_call_ms_host": cull_ms, "mesh_ms_culling_off": ms_off, "mesh_ms_culling_on": ms_on,
+                               "same_vertices": bool(nv_on == nv_off),
+                               "note": "reported beside, never inside, the headline; every culled span is empty in the CPU oracle (tests/test_configs.py)"}
+    del mc
+    torch.cuda.empty_cache()
     # small batches: the drop-in's steady state (64 leaves at start, 8 per split): host buffers, wall clock per call
     small = {}
     v = np.empty(700_000, dtype=cb.VERTEX_DTYPE); idx = np.empty(4_200_000, dtype=np.uint32)

@@ -6,15 +6,15 @@ naive-surface-nets mesh extraction, as hand-written CUDA kernels behind a C ABI
 reference's `Shape` / `MeshBuffer` / `octree::Span` interface over that ABI.
 """
 from ._lib import (CantucciError, Context, MultiContext, VERTEX_DTYPE, default_context, lib, shard_plan, LIB_PATH)
-from .mesh import (MeshBatch, MeshBuffer, MultiMeshBatch, Timings, generate_for_boxes, generate_for_boxes_multi,
-                   sample_grids, sample_signs)
+from .mesh import (MeshBatch, MeshBuffer, MultiMeshBatch, Timings, cull_spans, generate_for_boxes,
+                   generate_for_boxes_multi, sample_grids, sample_signs)
 from .octree import Octree, Span, create_spans, spans_array, startup_tree, tile_volume
 from .shape import Mandelbulb, Shape, Sphere
 from .shape_mesh import ShapeMesh
 
 __all__ = [
     "CantucciError", "Context", "MultiContext", "VERTEX_DTYPE", "default_context", "lib", "shard_plan", "LIB_PATH",
-    "MeshBatch", "MeshBuffer", "MultiMeshBatch", "Timings", "generate_for_boxes", "generate_for_boxes_multi",
+    "MeshBatch", "MeshBuffer", "MultiMeshBatch", "Timings", "cull_spans", "generate_for_boxes", "generate_for_boxes_multi",
     "sample_grids", "sample_signs",
     "Octree", "Span", "create_spans", "spans_array", "startup_tree", "tile_volume",
     "Mandelbulb", "Shape", "Sphere", "ShapeMesh",

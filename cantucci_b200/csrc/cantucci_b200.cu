@@ -11,6 +11,7 @@
 #include <immintrin.h>
 #endif
 #include <condition_variable>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1348,6 +1349,50 @@ int ctc_ctx_coalescing_stats(ctc_ctx* ctx, uint64_t* batches, uint64_t* requests
     if (batches) *batches = ctx->batches;
     if (requests) *requests = ctx->batched_requests;
     return CTC_OK;
+}
+
+// DE-bound span culling.  The distance estimate at a span's centre bounds how close the surface can
+// be (Shape::min_distance_from, shape/mod.rs:26-37: "a lower bound of the distance"); a span whose skirt-expanded
+// box lies inside that ball has an all-positive sample grid and an empty mesh.  Shapes with an upper bound as well
+// (Sphere, sphere.rs:37-39) also drop the spans that lie entirely inside.  keep[i] = 0: span i needs no meshing.
+int ctc_cull_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                   float safety, uint8_t* keep) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return guarded(ctx, [&]() -> int {
+        ShapeDev sh; uint32_t lg;
+        int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+        rc = check_spans(ctx, spans, nspans, resolution, &lg); if (rc) return rc;
+        if (nspans == 0) return CTC_OK;
+        if (!keep) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "keep is NULL");
+        if (!(safety >= 1.0f)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "safety must be >= 1");
+        CK(cudaSetDevice(ctx->device));
+        std::vector<float> centres(3 * nspans), reach(nspans), d(nspans);
+        for (size_t i = 0; i < nspans; ++i) {
+            double r2 = 0.0;
+            for (int c = 0; c < 3; ++c) {
+                const double ext = (double)spans[i].end[c] - (double)spans[i].start[c];
+                const double half = 0.5 * ext + ext / (double)resolution;       // half extent + the one-cell skirt (buffer.rs:64-67)
+                centres[3 * i + c] = (float)(0.5 * ((double)spans[i].start[c] + (double)spans[i].end[c]));
+                r2 += half * half;
+            }
+            reach[i] = (float)(std::sqrt(r2) * 1.0001);       // (rounding of the centre and of the sample positions)
+        }
+        ctc_shape exact = *shape;
+        exact.flags &= ~(uint32_t)CTC_MATH_FAST;
+        CK(ctx->pts_in.ensure(nspans * 12)); CK(ctx->pts_out.ensure(nspans * 4));
+        CK(cudaMemcpyAsync(ctx->pts_in.p, centres.data(), nspans * 12, cudaMemcpyHostToDevice, ctx->stream));
+        rc = de_batch_impl(ctx, &exact, ctx->pts_in.as<float>(), nspans, ctx->pts_out.as<float>()); if (rc) return rc;
+        CK(cudaMemcpyAsync(d.data(), ctx->pts_out.p, nspans * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const bool two_sided = shape->kind == CTC_SHAPE_SPHERE;         // max_distance_from is Some(..) (sphere.rs:37)
+        for (size_t i = 0; i < nspans; ++i) {
+            const bool outside = d[i] > safety * reach[i];
+            const bool inside = two_sided && -d[i] > reach[i];
+            keep[i] = (outside || inside) ? 0 : 1;                       // (NaN compares false: kept)
+        }
+        return CTC_OK;
+    });
 }
 
 int ctc_ray_march(ctc_ctx* ctx, const ctc_shape* shape, const float* origin, const float* dir, size_t n,

@@ -96,17 +96,41 @@ def sample_signs(spans, shape: Shape, resolution: int, ctx: _lib.Context | None 
     return out
 
 
+def cull_spans(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = None, safety: float = 2.0) -> np.ndarray:
+    """DE-bound span culling (ctc_cull_spans): boolean mask of the spans that still need meshing.  A span is
+    dropped when the distance estimate at its centre exceeds `safety` x the half-diagonal of its skirt-expanded
+    box (and, for shapes with an upper bound, when it lies entirely inside).  Not part of the reference; never
+    applied implicitly."""
+    ctx = ctx or _lib.default_context()
+    arr = spans_array(spans)
+    _check_args(arr, resolution)
+    keep = np.ones(arr.shape[0], dtype=np.uint8)
+    sh = shape._ctc_shape()
+    ctx.check(_lib.lib().ctc_cull_spans(ctx.handle, C.byref(sh), arr.ctypes.data, arr.shape[0], resolution,
+                                        C.c_float(safety), keep.ctypes.data))
+    return keep.astype(bool)
+
+
 def generate_for_boxes(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = None,
                        vcap: int | None = None, icap: int | None = None, out_v: np.ndarray | None = None,
-                       out_i: np.ndarray | None = None):
+                       out_i: np.ndarray | None = None, cull: bool = False):
     """generate_for_box for every span in ONE batched call -> (MeshBatch, Timings).
 
     Output capacity is guessed from the resolution and retried with the exact
     required size when the library reports CTC_ERR_OVERFLOW.  A lerp-factor
-    failure raises AssertionError like the reference's panic (math.rs:19)."""
+    failure raises AssertionError like the reference's panic (math.rs:19).
+    cull = True (not in the reference): spans the DE bound proves empty (cull_spans) are not meshed at all;
+    they come back as empty meshes."""
     ctx = ctx or _lib.default_context()
     arr = spans_array(spans)
     _check_args(arr, resolution)
+    if cull and arr.shape[0]:
+        keep = cull_spans(arr, shape, resolution, ctx)
+        if not keep.all():
+            sub, t = generate_for_boxes(np.ascontiguousarray(arr[keep]), shape, resolution, ctx, vcap, icap, out_v, out_i)
+            # offsets of a culled span = those of the next kept one (an empty range)
+            pos = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+            return MeshBatch(sub.vertices, sub.indices, sub.v_off[pos], sub.i_off[pos]), t
     ns = arr.shape[0]
     if vcap is None:
         vcap = max(1024, ns * 8 * resolution * resolution)

@@ -193,6 +193,16 @@ CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indi
 
 /* ---- focus rays: ShapeMesh::get_focii's sphere tracing (src/mesh/mod.rs:229-241) ---- */
 
+/* DE-bound span culling (not in the reference).  keep[i] = 0 when span i needs no meshing: the
+ * distance estimate at its centre (exact arithmetic) exceeds `safety` times the half-diagonal of the skirt-
+ * expanded span, i.e. the surface cannot reach it (Shape::min_distance_from is "a lower bound of the distance",
+ * shape/mod.rs:26-37); for shapes with an upper bound too (Sphere, max_distance_from = min_distance_from,
+ * sphere.rs:37-39) also when the span lies entirely inside.  The Mandelbulb estimate is not a rigorous bound:
+ * safety >= 1 is the caller's margin (the host mirror uses 2); tests check every culled span of the BASELINE
+ * configs against the CPU oracle.  Culling is never applied implicitly by the mesh calls. */
+CTC_API int ctc_cull_spans(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                           uint32_t resolution, float safety, uint8_t *keep);
+
 /* n rays (origin, unit direction; packed xyz, HOST pointers).  Each ray repeats
  * `d = DE(pos); pos += dir * d; if d < epsilon { hit }` up to max_steps times
  * (the reference uses EPSILON = 1e-6, MAX_ITERS = 100).  out_pos: n packed xyz,

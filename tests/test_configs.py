@@ -222,3 +222,46 @@ def test_resolution_1024_single_span_grid(oracle, ctx):
     assert bits(got)[-2] == 0xFFC00000                      # the origin
     rc = _lib.lib().ctc_sample_grids_device(ctx.handle, C.byref(sh), bbox.ctypes.data, 1, 2048, g.data_ptr())
     assert rc == _lib.CTC_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.gpu
+def test_de_bound_culling_only_drops_spans_the_oracle_finds_empty(oracle, ctx):
+    """cull_spans drops a span when the distance estimate at its centre exceeds twice the half-
+    diagonal of its skirt-expanded box.  Every culled span must have an EMPTY mesh in the CPU oracle -- on the
+    startup octree (config 1), the depth-6 refinement (config 3) and the 1024^3 volume -- and meshing with
+    cull = True must return exactly the un-culled result.  Sphere: spans entirely inside are dropped too."""
+    import cantucci_b200 as cb
+    from cantucci_b200 import refine
+    shape = cb.Mandelbulb.classic(6, 2.5)
+    osh = oracle.mandelbulb(8, 6, 2.5)
+    startup = cb.spans_array([n.span for n in cb.startup_tree(shape.bounding_box()).leaves()])
+    leaves, _ = refine.config3_spans(shape, 6, ctx)
+    volume = cb.tile_volume(cb.Span((-1.2,) * 3, (1.2,) * 3), 16)
+    culled_total = 0
+    for name, spans in (("config1", startup), ("config3", leaves), ("volume", volume)):
+        keep = cb.cull_spans(spans, shape, 64, ctx)
+        dropped = np.ascontiguousarray(spans[~keep])
+        culled_total += len(dropped)
+        if len(dropped):
+            v, i, v_off, i_off, planes, panicked, _ = oracle.generate_for_boxes_flat_mt(osh, dropped, 64, oracle.hardware_threads(), signs=True)
+            assert int(v_off[-1]) == 0 and int(i_off[-1]) == 0, (name, int(v_off[-1]))
+            assert not planes.any(), name                      # every sample of a culled span is outside
+    assert culled_total > 0
+    keep = cb.cull_spans(volume, shape, 64, ctx)
+    assert 0.05 < (~keep).mean() < 0.9
+    sub = volume[::7]
+    a, _ = cb.generate_for_boxes(sub, shape, 64, ctx)
+    b, _ = cb.generate_for_boxes(sub, shape, 64, ctx, cull=True)
+    assert np.array_equal(a.v_off, b.v_off) and np.array_equal(a.i_off, b.i_off)
+    assert np.array_equal(a.indices, b.indices) and np.array_equal(a.vertices.view(np.uint32), b.vertices.view(np.uint32))
+    # Sphere (two-sided bound): spans far outside AND spans deep inside go
+    sph = cb.Sphere((0.0, 0.0, 0.0), 1.0)
+    tiles = cb.tile_volume(cb.Span((-1.2,) * 3, (1.2,) * 3), 8)
+    keep = cb.cull_spans(tiles, sph, 32, ctx)
+    centre = 0.5 * (tiles[:, :3] + tiles[:, 3:])
+    rad = np.linalg.norm(centre, axis=1)
+    assert (~keep)[rad < 0.3].all() and keep[np.abs(rad - 1.0) < 0.1].all()
+    a, _ = cb.generate_for_boxes(tiles, sph, 32, ctx)
+    b, _ = cb.generate_for_boxes(tiles, sph, 32, ctx, cull=True)
+    assert np.array_equal(a.v_off, b.v_off) and np.array_equal(a.indices, b.indices)
+    assert np.array_equal(np.diff(a.v_off.astype(np.int64))[~keep], np.zeros((~keep).sum(), dtype=np.int64))
