@@ -628,9 +628,78 @@ __device__ __forceinline__ float2 mandelbulb_de_fast_p8_column_pair(const ShapeD
     p8_column_pair_impl<kBand>(s, px_, py_, pz, c, d, suspect);
     return d;
 }
+// ---------------------------------------------------------------------------
+// FAST generic powers that are powers of two (config 4's P = 2, 4, 16): the same trig-free complex powers as
+// mandelbulb_de_fast_generic below, but with the K = log2 P squarings unrolled and two samples per thread in
+// packed FP32, like the power-8 path:
+//   (z + i w)^P = r^P (cos P.theta + i sin P.theta),   ((x + i y)/w)^P = cos P.phi + i sin P.phi
+//   X = r^P sin P.theta cos P.phi + px,  Y = r^P sin P.theta sin P.phi + py,  Z = r^P cos P.theta + pz
+// (mandelbulb.rs:128-146; no "- y8" quirk here: the generic step is the true map).  No sign band (exact mode
+// itself is a tolerance path for these powers): only the z-axis / NaN rule marks a half suspect.
+// ---------------------------------------------------------------------------
+template <int K, class V>
+__device__ __forceinline__ void pow2_step(V& zx, V& zy, V& zz, V z2, V w2, V px, V py, V pz, V& iw) {
+    using L = Lanes<V>;
+    iw = L::rsqrt(w2);
+    const V w = L::mul(w2, iw);
+    V er = L::sub(z2, w2), ei = L::mul(L::mul(zz, w), L::bc(2.0f));                 // (z + i w)^2
+    const V u = L::mul(zx, iw), v = L::mul(zy, iw);
+    V ar = L::fms(u, u, L::mul(v, v)), ai = L::mul(L::mul(u, v), L::bc(2.0f));      // ((x + i y) / w)^2
+#pragma unroll
+    for (int sq = 1; sq < K; ++sq) {
+        const V t = L::fms(er, er, L::mul(ei, ei)); ei = L::mul(L::mul(er, ei), L::bc(2.0f)); er = t;
+        const V a = L::fms(ar, ar, L::mul(ai, ai)); ai = L::mul(L::mul(ar, ai), L::bc(2.0f)); ar = a;
+    }
+    zx = L::fma(ei, ar, px); zy = L::fma(ei, ai, py); zz = L::add(er, pz);
+}
+
+// dr = P r^(P-1) dr + 1 with P = 2^K, from r^2
+template <int K, class V>
+__device__ __forceinline__ V pow2_dr(V r2, V dr) {
+    using L = Lanes<V>;
+    V acc = L::sqrt(r2), cur = r2;                       // r^(2^j - 1) after j rounds
+#pragma unroll
+    for (int j = 1; j < K; ++j) { acc = L::mul(acc, cur); if (j + 1 < K) cur = L::mul(cur, cur); }
+    return L::fma(L::mul(acc, L::bc((float)(1 << K))), dr, L::bc(1.0f));
+}
+
+template <int K>
+__device__ __forceinline__ void pow2_pair_impl(const ShapeDev& s, float2 px, float2 py, float2 pz, float2& d, uint32_t& suspect) {
+    using L = Lanes<float2>;
+    constexpr bool kBand = false;
+    const float bail2 = s.bail2;
+    float2 zx = px, zy = py, zz = pz, dr = L::bc(1.0f), r2;
+    Amp ampa = amp_init(), ampb = amp_init();
+    uint32_t done = 0u, left = s.max_iters;
+    for (;;) {
+        const float2 z2 = L::mul(zz, zz);
+        const float2 w2 = L::fma(zx, zx, L::mul(zy, zy));
+        r2 = L::add(w2, z2);
+        CTC_PAIR_RADIUS_TEST()
+        dr = pow2_dr<K, float2>(r2, dr);
+        if (--left == 0u) break;
+        float2 iw;
+        pow2_step<K, float2>(zx, zy, zz, z2, w2, px, py, pz, iw);
+        ampa.iwmax = max(ampa.iwmax, __float_as_int(iw.x));
+        ampb.iwmax = max(ampb.iwmax, __float_as_int(iw.y));
+    }
+    CTC_PAIR_TAIL()
+}
+
+// FAST DE of two points for P = 2^K.  Bit k of `suspect`: half k needs the exact path.
+template <int K>
+__device__ __forceinline__ float2 mandelbulb_de_fast_pow2_pair(const ShapeDev& s, float2 px, float2 py, float2 pz, uint32_t& suspect) {
+    float2 d = make_float2(0.0f, 0.0f);
+    suspect = 0u;
+    pow2_pair_impl<K>(s, px, py, pz, d, suspect);
+    return d;
+}
 #undef CTC_PAIR_ESCAPE
 #undef CTC_PAIR_RADIUS_TEST
 #undef CTC_PAIR_TAIL
+
+// log2 P when the packed power-of-two path serves P (2, 4, 16; 8 is the polynomial variant), else 0
+__device__ __forceinline__ int pow2_path(uint32_t P) { return P == 2u ? 1 : P == 4u ? 2 : P == 16u ? 4 : 0; }
 
 // FAST generic-power DE of one sample (config 4's P = 2, 4, 16, ...): trig-free complex binary powers
 //   (z + i w)^P = r^P (cos P.theta + i sin P.theta),   ((x + i y)/w)^P = cos P.phi + i sin P.phi

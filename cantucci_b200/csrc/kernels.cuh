@@ -245,6 +245,18 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
             // exact arithmetic: hoist the x/y-only sub-expressions of the first iteration (bit-identical CSE)
             const ColumnExactP8 col = column_exact_p8(px, py);
             CTC_K1_STEPS(d.x = mandelbulb_de_exact_p8_column(sh, px, py, pz.x, col); d.y = mandelbulb_de_exact_p8_column(sh, px, py, pz.y, col);)
+        } else if (kFast && kVariant == kVarGeneric && pow2_path(sh.power) != 0) {
+            // P = 2, 4, 16: packed pairs with the squarings unrolled (warp-uniform switch)
+            const float2 px2 = make_float2(px, px), py2 = make_float2(py, py);
+#define CTC_K1_POW2(K)                                                                                          \
+            CTC_K1_STEPS(                                                                                       \
+                uint32_t susp;                                                                                  \
+                d = mandelbulb_de_fast_pow2_pair<K>(sh, px2, py2, pz, susp);                                    \
+                if (susp & 1u) d.x = mandelbulb_de_exact_cold<false>(sh, px, py, pz.x);                         \
+                if (susp & 2u) d.y = mandelbulb_de_exact_cold<false>(sh, px, py, pz.y);)
+            const int k = pow2_path(sh.power);
+            if (k == 1) { CTC_K1_POW2(1) } else if (k == 2) { CTC_K1_POW2(2) } else { CTC_K1_POW2(4) }
+#undef CTC_K1_POW2
         } else {
             CTC_K1_STEPS(d.x = shape_de<kFast, kVariant>(sh, px, py, pz.x); d.y = shape_de<kFast, kVariant>(sh, px, py, pz.y);)
         }
@@ -668,6 +680,21 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
                 de[k] = d2.x; de[k + 1] = d2.y;
                 if (susp & 1u) de[k] = mandelbulb_de_exact_cold<true>(sh, ex[k], ey[k], ez[k]);
                 if (susp & 2u) de[k + 1] = mandelbulb_de_exact_cold<true>(sh, ex[k + 1], ey[k + 1], ez[k + 1]);
+            }
+        } else if (kFast && kVariant == kVarGeneric && pow2_path(sh.power) != 0) {
+            // P = 2, 4, 16: the +-delta evaluations as packed pairs, like the power-8 branch
+            de[0] = shape_de<true, kVarGeneric, false>(sh, ex[0], ey[0], ez[0]);
+            const int lp = pow2_path(sh.power);
+#pragma unroll
+            for (int k = 1; k < 7; k += 2) {
+                uint32_t susp;
+                const float2 ax = make_float2(ex[k], ex[k + 1]), ay = make_float2(ey[k], ey[k + 1]), az = make_float2(ez[k], ez[k + 1]);
+                const float2 d2 = lp == 1 ? mandelbulb_de_fast_pow2_pair<1>(sh, ax, ay, az, susp)
+                                : lp == 2 ? mandelbulb_de_fast_pow2_pair<2>(sh, ax, ay, az, susp)
+                                          : mandelbulb_de_fast_pow2_pair<4>(sh, ax, ay, az, susp);
+                de[k] = d2.x; de[k + 1] = d2.y;
+                if (susp & 1u) de[k] = mandelbulb_de_exact_cold<false>(sh, ex[k], ey[k], ez[k]);
+                if (susp & 2u) de[k + 1] = mandelbulb_de_exact_cold<false>(sh, ex[k + 1], ey[k + 1], ez[k + 1]);
             }
         } else {
 #pragma unroll
