@@ -278,6 +278,13 @@ __device__ __forceinline__ float fast_sqrt(float a) { float r; asm("sqrt.approx.
 __device__ __forceinline__ float fast_rsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ float fast_lg2(float a) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 
+// unroll factor of the packed pair loop (A/B on the benched volume, scripts/gpu_ab.py)
+#ifndef CTC_PAIR_UNROLL
+#define CTC_PAIR_UNROLL 2
+#endif
+#define CTC_PRAGMA_(x) _Pragma(#x)
+#define CTC_PRAGMA_UNROLL(n) CTC_PRAGMA_(unroll n)
+
 template <class V> struct Lanes;
 
 template <> struct Lanes<float> {
@@ -551,7 +558,7 @@ __device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float
     using L = Lanes<float2>;
     const float bail2 = s.bail2;
     float2 r2;
-#pragma unroll 2
+CTC_PRAGMA_UNROLL(CTC_PAIR_UNROLL)
     for (;;) {
         const float2 z2 = L::mul(zz, zz);
         const float2 w2 = L::fma(zx, zx, L::mul(zy, zy));

@@ -53,6 +53,24 @@ class GatheredMeshes:
     n_indices: int
 
 
+class ResidentMeshes:
+    """One GPU's result, left in device memory (same fields as GatheredMeshes); the per-span [begin, end) tables
+    are copied to the host on first use."""
+
+    def __init__(self, vertices, indices, v_off_dev, i_off_dev, n_vertices: int, n_indices: int):
+        self.vertices, self.indices, self.n_vertices, self.n_indices = vertices, indices, n_vertices, n_indices
+        self._v_off, self._i_off, self._tables = v_off_dev, i_off_dev, None
+
+    def _build(self):
+        if self._tables is None:
+            ov, oi = self._v_off.cpu().numpy(), self._i_off.cpu().numpy()
+            self._tables = (np.stack([ov[:-1], ov[1:]], 1), np.stack([oi[:-1], oi[1:]], 1))
+        return self._tables
+
+    span_v = property(lambda self: self._build()[0])
+    span_i = property(lambda self: self._build()[1])
+
+
 class DeviceMesher:
     """Runs ctc_mesh_spans_device on torch-owned device buffers of one rank."""
 
@@ -118,10 +136,8 @@ class SpanScheduler:
         if world == 1:
             m.launch(shape_struct, local, resolution)
             nv, ni, _ = m.result(allow_lerp_assert=allow_lerp_assert)
-            off_v = m.v_off[: nspans + 1].cpu().numpy()
-            off_i = m.i_off[: nspans + 1].cpu().numpy()
-            return GatheredMeshes(m.v[:nv], m.i[:ni], np.stack([off_v[:-1], off_v[1:]], 1),
-                                  np.stack([off_i[:-1], off_i[1:]], 1), nv, ni)
+            # results stay resident in HBM: the per-span tables are fetched when (and if) somebody reads them
+            return ResidentMeshes(m.v[:nv], m.i[:ni], m.v_off[: nspans + 1], m.i_off[: nspans + 1], nv, ni)
         # rank 0 meshes straight into the head of the gathered buffers
         if rank == 0:
             m.launch(shape_struct, local, resolution, v=self.total_v, i=self.total_i,

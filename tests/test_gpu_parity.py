@@ -279,6 +279,45 @@ def test_fast_mode_mesh_within_tolerance_of_oracle(oracle, ctx):
     assert mismatched / total < 1e-4, (mismatched, total)
 
 
+def test_fast_mode_is_sign_exact_config1_index_buffers_equal_the_golden_sha(ctx):
+    """Sign-exact fast mode: suspects are re-evaluated exactly, so the topology of config 1 (64 startup leaves)
+    is the CPU path's -- per-span counts and the SHA-256 of all index bytes equal the golden fixture's."""
+    import cantucci_b200 as cb
+    spans = startup_leaves()
+    batch, t = cb.generate_for_boxes(spans, cb.Mandelbulb.classic(6, 2.5, fast=True), 64, ctx)
+    gold = json.load(open(os.path.join(GOLD, "config1_startup.json")))
+    assert [int(batch.v_off[k + 1] - batch.v_off[k]) for k in range(64)] == gold["vertices_per_span"]
+    assert [int(batch.i_off[k + 1] - batch.i_off[k]) // 6 for k in range(64)] == gold["quads_per_span"]
+    assert hashlib.sha256(batch.indices.tobytes()).hexdigest() == gold["indices_sha256"]
+    suspects, fixups = ctx.mesh_fixups()
+    assert suspects > 0                        # the band did select samples for the exact re-evaluation
+
+
+def test_fast_mode_full_benched_volume_passes_the_parity_gate(oracle, ctx):
+    """The measurement's own gate (bench.parity_gate) as a test, on ALL 4096 spans of the benched 1024^3 volume
+    in the benched (fast) mode: zero sign mismatches over 1.125 G samples, equal per-span counts, identical
+    index buffers, and positions / NORMALS / distance_from_surface within the stated tolerances."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import cantucci_b200 as cb
+    spans = bench.workload_spans()
+    ora = bench.oracle_volume(spans)
+    shape = cb.Mandelbulb.classic(bench.MAX_ITERS, bench.BAILOUT, fast=True)
+    gv, gi, gvo, gio, planes = bench.gpu_volume_host(ctx, shape, spans, vcap=int(ora["v_off"][-1] * 1.05) + 1024,
+                                                     icap=int(ora["i_off"][-1] * 1.05) + 6144)
+    par = bench.parity_gate(gv, gi, gvo, gio, planes, ora, spans, exact=False)
+    assert par["sign_mismatches"] == 0 and par["spans_with_different_counts"] == 0, par
+    assert par["index_buffers_identical"] and par["indices_sha256"] == par["indices_sha256_reference"], par
+    assert par["vertices_compared"] == par["vertices_reference"] == 13505557
+    for k, tol in bench.PARITY_TOL.items():
+        key = {"position_cells_p99": "position_err_cells_p99", "position_cells_p999": "position_err_cells_p999",
+               "normal_p99": "normal_err_p99", "normal_p999": "normal_err_p999",
+               "distance_cells_p99": "distance_err_cells_p99", "distance_cells_p999": "distance_err_cells_p999"}[k]
+        assert par[key] <= tol, (k, par[key], tol)
+    assert par["normals_nan_in_one"] == 0 and par["ok"], par
+
+
 # ---------------------------------------------- full-size properties ------
 def test_dense_512_grid_and_the_reference_panic(oracle, ctx):
     """BASELINE config 2 (dense 512^3, one bbox span).  Pass 1 is checked against facts that do
