@@ -941,6 +941,13 @@ int ctc_ctx_host_index_wire_stats(ctc_ctx* ctx, uint64_t* calls, uint64_t* fallb
     return CTC_OK;
 }
 
+int ctc_expand_quads_host(const void* records, size_t nquads, uint32_t* idx) {
+    if (nquads == 0) return CTC_OK;
+    if (!records || !idx || (reinterpret_cast<uintptr_t>(records) & 7u) || (reinterpret_cast<uintptr_t>(idx) & 3u)) return CTC_ERR_INVALID_ARGUMENT;
+    expand_quads_host(static_cast<const uint2*>(records), nquads, idx);
+    return CTC_OK;
+}
+
 int ctc_expand_quads(ctc_ctx* ctx, const void* d_records, size_t nquads, uint32_t* d_idx) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);

@@ -274,6 +274,10 @@ CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
  * on the context's stream). */
 CTC_API int ctc_ctx_set_index_wire(ctc_ctx *ctx, int packed_quads);
 CTC_API int ctc_expand_quads(ctc_ctx *ctx, const void *d_records, size_t nquads, uint32_t *d_idx);
+/* The same widening on the calling HOST thread (host pointers; no context, no GPU): what the host-side pool of
+ * ctc_mesh_spans runs per piece.  A consumer that asked for packed records (ctc_ctx_set_index_wire) can widen
+ * them itself with this. */
+CTC_API int ctc_expand_quads_host(const void *records, size_t nquads, uint32_t *idx);
 /* Packed index wire towards a PEER GPU (ctc_ctx_set_index_wire(ctx, 1), device destination): after every launch
  * group's records ctc_mesh_spans also puts one 64-bit progress word {done:1 | call epoch:23 | quads so far:40}
  * at d_progress_word (memory of the destination GPU), in order behind the records, and a last one with the
