@@ -467,12 +467,17 @@ void launch_sample(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, uint3
     const size_t R2 = (size_t)R * R, R3 = R2 * R;
     // (small batches -- the drop-in's steady state is 8 leaves per split -- walk 32: twice the warps, half the
     // dependent chain, the SMs are far from full anyway)
+#ifdef CTC_K1_WALK32
+    const uint32_t lgw = 0u;
+#else
     const uint32_t lgw = (lg >= 6 && (size_t)nspans * R3 >= ((size_t)1 << 23)) ? 1u : 0u;
+#endif
     const size_t warp_blocks = lg >= 5 ? (R3 + 2 * R2) / (256u << lgw) : 0;
-    const uint32_t core_blocks = (uint32_t)((warp_blocks + 7) / 8);
+    constexpr size_t kWarps = kK1Threads / 32;
+    const uint32_t core_blocks = (uint32_t)((warp_blocks + kWarps - 1) / kWarps);
     const size_t rest = core_blocks ? R2 + 3 * (size_t)R + 1 : n3;
-    dim3 grid(core_blocks + (unsigned)((rest + kThreads - 1) / kThreads), nspans);
-    sample_grids_kernel<kFast, kVariant><<<grid, kThreads, 0, stream>>>(sh, geom, R, lg, 1.0f / (float)R, 8.0f / (float)R, grids, stride,
+    dim3 grid(core_blocks + (unsigned)((rest + kK1Threads - 1) / kK1Threads), nspans);
+    sample_grids_kernel<kFast, kVariant><<<grid, kK1Threads, 0, stream>>>(sh, geom, R, lg, 1.0f / (float)R, 8.0f / (float)R, grids, stride,
                                                                         sign_bits, sign_stride, core_blocks, lgw, sl);
     ctx->launches++;
 }

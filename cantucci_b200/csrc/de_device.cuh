@@ -558,7 +558,9 @@ __device__ __forceinline__ void p8_pair_loop(const ShapeDev& s, float2 px, float
     using L = Lanes<float2>;
     const float bail2 = s.bail2;
     float2 r2;
-CTC_PRAGMA_UNROLL(CTC_PAIR_UNROLL)
+    // (A/B on the benched volume: K1 -- the band-tracking instantiation -- is fastest unrolled 3x, E3 2x)
+    constexpr int kUnroll = kBand ? CTC_PAIR_UNROLL + 1 : CTC_PAIR_UNROLL;
+#pragma unroll kUnroll
     for (;;) {
         const float2 z2 = L::mul(zz, zz);
         const float2 w2 = L::fma(zx, zx, L::mul(zy, zy));

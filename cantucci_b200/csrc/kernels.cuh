@@ -50,6 +50,12 @@ struct MeshState {
 };
 
 constexpr int kThreads = 256;
+// K1's CTA size (A/B on the benched volume, scripts/gpu_ab.py: 256 threads 4.49 ms, 128: 4.40, 64: 4.45 -- four warp
+// walks per CTA retire and refill an SM's slots more evenly than eight)
+#ifndef CTC_K1_THREADS
+#define CTC_K1_THREADS 128
+#endif
+constexpr int kK1Threads = CTC_K1_THREADS;
 constexpr uint32_t kMaxChunkWords = 256;  // one word per thread in E1+E2
 
 // ---------------------------------------------------------------------------
@@ -131,7 +137,7 @@ struct SuspectList {
 #endif
 
 template <bool kFast, int kVariant>
-__global__ void __launch_bounds__(kThreads, kFast && kVariant == kVarP8 ? CTC_K1_MINBLOCKS : 1)
+__global__ void __launch_bounds__(kK1Threads, kFast && kVariant == kVarP8 ? CTC_K1_MINBLOCKS * (256 / kK1Threads) : 1)
 sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, uint32_t lg, float inv_r, float dvz8,
                     float* __restrict__ grids, size_t grid_stride,
                     uint32_t* __restrict__ sign_bits, uint32_t sign_stride /* words per span, 0 = no plane */,
@@ -145,7 +151,7 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
         // warp-blocks of L = 32 << lgw z-samples: [0, R^3/(8L)) core 2x4xL; then R^2/(8L) blocks 1x8xL of
         // the x = R face; then R^2/(8L) blocks 8x1xL of the y = R face.  Each is walked in L/8 brick steps.
         const uint32_t lane = threadIdx.x & 31u;
-        const uint32_t wb = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+        const uint32_t wb = blockIdx.x * (kK1Threads / 32) + (threadIdx.x >> 5);
         const uint32_t lgL = 5u + lgw;
         const uint32_t n_core = 1u << (3 * lg - 3 - lgL), n_face = 1u << (2 * lg - 3 - lgL);
         if (wb >= n_core + 2u * n_face) return;
@@ -265,7 +271,7 @@ sample_grids_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, uint32_t R, 
     }
     // one thread per remaining sample: everything when R < 32, else the z = R face, the three edges
     // x=y=R / x=z=R / y=z=R and the corner (R^2 + 3R + 1 samples)
-    const uint32_t i = (blockIdx.x - core_blocks) * kThreads + threadIdx.x;
+    const uint32_t i = (blockIdx.x - core_blocks) * kK1Threads + threadIdx.x;
     uint32_t x, y, z;
     if (core_blocks == 0u) {
         if (i >= n * n * n) return;
