@@ -575,7 +575,7 @@ template <bool kFast, int kVariant>
 void launch_vertex(ctc_ctx* ctx, const ShapeDev& sh, const SpanGeom* geom, const float* grids, size_t stride, uint32_t R,
                    uint32_t lg, const uint32_t* cell_of, uint32_t cell_cap, uint8_t* neg8, MeshState* st, uint32_t span0, float* out_v,
                    unsigned long long vcap, unsigned blocks, cudaStream_t stream) {
-    vertex_kernel<kFast, kVariant><<<blocks, kThreads, 0, stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap, neg8,
+    vertex_kernel<kFast, kVariant><<<blocks * (kThreads / kE3Threads), kE3Threads, 0, stream>>>(sh, geom, grids, stride, R, lg, cell_of, cell_cap, neg8,
                                                                          st, span0, out_v, vcap);
     ctx->launches++;
 }

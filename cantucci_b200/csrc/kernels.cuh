@@ -56,6 +56,13 @@ constexpr int kThreads = 256;
 #define CTC_K1_THREADS 128
 #endif
 constexpr int kK1Threads = CTC_K1_THREADS;
+#ifndef CTC_E3_THREADS
+#define CTC_E3_THREADS 256
+#endif
+#ifndef CTC_E3_MINBLOCKS
+#define CTC_E3_MINBLOCKS (4 * 256 / CTC_E3_THREADS)
+#endif
+constexpr int kE3Threads = CTC_E3_THREADS;
 constexpr uint32_t kMaxChunkWords = 256;  // one word per thread in E1+E2
 
 // ---------------------------------------------------------------------------
@@ -563,7 +570,7 @@ emit_lists_kernel(const uint32_t* __restrict__ sign_bits, uint32_t sign_stride, 
 // cells (the count lives on the device, no host sync).  One thread per vertex.
 // ---------------------------------------------------------------------------
 template <bool kFast, int kVariant>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kE3Threads, CTC_E3_MINBLOCKS)
 vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __restrict__ grids, size_t grid_stride,
               uint32_t R, uint32_t lg, const uint32_t* __restrict__ cell_of, uint32_t cell_cap, uint8_t* __restrict__ neg8,
               MeshState* st, uint32_t span0, float* __restrict__ out_v, unsigned long long vcap) {
@@ -572,7 +579,7 @@ vertex_kernel(ShapeDev sh, const SpanGeom* __restrict__ geom, const float* __res
     const unsigned long long base_v = st->group_base_v;
     const uint32_t n = R + 1u;
     const uint32_t lg3 = 3 * lg;
-    for (uint32_t v = blockIdx.x * kThreads + threadIdx.x; v < nv; v += gridDim.x * kThreads) {
+    for (uint32_t v = blockIdx.x * kE3Threads + threadIdx.x; v < nv; v += gridDim.x * kE3Threads) {
         const unsigned long long slot = base_v + v;
         if (slot >= vcap) continue;
         const uint32_t cell = cell_of[v];
