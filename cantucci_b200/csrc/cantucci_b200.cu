@@ -122,8 +122,6 @@ __attribute__((target("avx2"))) void expand_quads_avx2(const uint2* __restrict__
 #endif
 
 void expand_quads_host(const uint2* rec, size_t n, uint32_t* out) {
-    static const bool skip = getenv("CANTUCCI_B200_EXPAND_SKIP") != nullptr;     // measurement aid: copy-only timing
-    if (skip) return;
 #if defined(__x86_64__) && defined(__GNUC__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
     if (have_avx2) { expand_quads_avx2(rec, n, out); return; }

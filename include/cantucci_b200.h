@@ -113,8 +113,8 @@ CTC_API void ctc_ctx_destroy(ctc_ctx *ctx);
 /* Adopt an external cudaStream_t (e.g. the host framework's current stream);
  * NULL restores the context's own stream. */
 CTC_API int ctc_ctx_set_stream(ctc_ctx *ctx, void *cuda_stream);
-/* Spans per internal launch group (0 = automatic, sized to keep a group's
- * sample grids L2-resident). */
+/* Spans per internal launch group (0 = automatic: about 512 MiB of sample grids per group, at least four
+ * groups per large call so that copies and extraction pipeline behind the next group's DE kernel). */
 CTC_API int ctc_ctx_set_group_spans(ctc_ctx *ctx, uint32_t spans_per_group);
 /* 1 (default): a launch group's extraction kernels run on a second, high-
  * priority stream concurrently with the next group's DE kernel.  0: strictly
@@ -292,7 +292,8 @@ CTC_API int ctc_ctx_set_wire_progress(ctc_ctx *ctx, void *d_progress_word);
  * with >= 65536 vertices makes the call repeat itself with u32 indices on the wire (counted in `fallbacks`).
  * Calls of fewer than 128 spans are not PCIe-bound and keep six u32 per quad (2: packed records for every call).
  * 0: always copy six u32 per quad.  Independently of this switch, buffers in PAGEABLE host memory are filled
- * through pinned landing buffers by the same host threads (calls of more than 8 spans). */
+ * through pinned landing buffers by the same host threads (calls of more than 8 spans).  The pool has half the
+ * hardware threads (shared out over the devices of a ctc_multi); CANTUCCI_B200_EXPAND_THREADS overrides the count. */
 CTC_API int ctc_ctx_set_host_index_wire(ctc_ctx *ctx, int packed_quads);
 CTC_API int ctc_ctx_host_index_wire_stats(ctc_ctx *ctx, uint64_t *calls, uint64_t *fallbacks, uint32_t *threads);
 
