@@ -716,6 +716,14 @@ def other_configs(ctx, cb, _lib, refine, torch, device, stream, DeviceMesher, no
                                "note": "reported beside, never inside, the headline; every culled span is empty in the CPU oracle (tests/test_configs.py)"}
     del mc
     torch.cuda.empty_cache()
+    # N4: the planned ray-marcher, one sphere-traced ray per pixel (ctc_render_device), 1920 x 1080
+    cam = cb.look_at_rays((1.8, 1.3, 2.2), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 40.0, 1920, 1080)
+    img = torch.empty((1080, 1920, 4), dtype=torch.float32, device=device)
+    ms_r = timed(lambda: ctx.check(L.ctc_render_device(ctx.handle, C.byref(sh), C.byref(cam), 1920, 1080, 100, C.c_float(1e-4), img.data_ptr())), 10)
+    hits = int((img[..., 3] >= 0).sum())
+    out["render_1920x1080"] = {"ms": ms_r, "frames_per_s": 1e3 / ms_r, "rays_per_s": 1920 * 1080 / (ms_r * 1e-3), "pixels_hit": hits,
+                               "max_steps": 100, "epsilon": 1e-4, "math": "fast"}
+    del img
     # small batches: the drop-in's steady state (64 leaves at start, 8 per split): host buffers, wall clock per call
     small = {}
     v = np.empty(700_000, dtype=cb.VERTEX_DTYPE); idx = np.empty(4_200_000, dtype=np.uint32)

@@ -10,6 +10,7 @@ from .mesh import (MeshBatch, MeshBuffer, MultiMeshBatch, Timings, cull_spans, g
                    generate_for_boxes_multi, sample_grids, sample_signs)
 from .octree import Octree, Span, create_spans, spans_array, startup_tree, tile_volume
 from .shape import Mandelbulb, Shape, Sphere
+from .render import CtcCameraRays, look_at_rays, pixel_rays, render, shade
 from .shape_mesh import ShapeMesh
 
 __all__ = [
@@ -18,4 +19,5 @@ __all__ = [
     "sample_grids", "sample_signs",
     "Octree", "Span", "create_spans", "spans_array", "startup_tree", "tile_volume",
     "Mandelbulb", "Shape", "Sphere", "ShapeMesh",
+    "CtcCameraRays", "look_at_rays", "pixel_rays", "render", "shade",
 ]

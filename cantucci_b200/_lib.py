@@ -70,7 +70,7 @@ EXPORTS = (
     "ctc_host_register", "ctc_host_unregister", "ctc_ctx_set_index_wire", "ctc_expand_quads",
     "ctc_ctx_set_fast_band", "ctc_mesh_fixups", "ctc_fast_sign_probe", "ctc_sample_signs",
     "ctc_ctx_set_kernel_timing", "ctc_mesh_kernel_times", "ctc_iteration_stats_points",
-    "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats", "ctc_ctx_set_host_index_wire", "ctc_ctx_host_index_wire_stats", "ctc_ctx_set_wire_progress", "ctc_cull_spans", "ctc_expand_quads_host",
+    "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats", "ctc_ctx_set_host_index_wire", "ctc_ctx_host_index_wire_stats", "ctc_ctx_set_wire_progress", "ctc_cull_spans", "ctc_expand_quads_host", "ctc_render", "ctc_render_device",
     "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
     "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
 )
@@ -163,6 +163,10 @@ def lib() -> C.CDLL:
     L.ctc_fast_sign_probe.argtypes = [vp, shp, spn, sz, u32, u64p, sz]
     L.ctc_ctx_set_coalescing.restype = C.c_int
     L.ctc_ctx_set_coalescing.argtypes = [vp, C.c_int]
+    L.ctc_render.restype = C.c_int
+    L.ctc_render.argtypes = [vp, shp, vp, u32, u32, u32, C.c_float, vp]
+    L.ctc_render_device.restype = C.c_int
+    L.ctc_render_device.argtypes = [vp, shp, vp, u32, u32, u32, C.c_float, vp]
     L.ctc_expand_quads_host.restype = C.c_int
     L.ctc_expand_quads_host.argtypes = [vp, sz, vp]
     L.ctc_cull_spans.restype = C.c_int

@@ -1433,6 +1433,52 @@ int ctc_ray_march(ctc_ctx* ctx, const ctc_shape* shape, const float* origin, con
     return CTC_OK;
 }
 
+// N4: sphere-traced image of the shape, one thread per pixel (render_kernel).
+static int render_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_camera_rays* cam, uint32_t width, uint32_t height,
+                       uint32_t max_steps, float epsilon, float* out, bool out_on_device) {
+    ShapeDev sh;
+    int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+    if (!cam || !out) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "NULL camera / output");
+    if (width == 0 || height == 0) return CTC_OK;
+    if ((size_t)width * height > ((size_t)1 << 28)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "image too large");
+    if (out_on_device && (reinterpret_cast<uintptr_t>(out) & 15u)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "output must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height;
+    float4* d_out = reinterpret_cast<float4*>(out);
+    if (!out_on_device) { CK(ctx->pts_out.ensure(n * sizeof(float4))); d_out = ctx->pts_out.as<float4>(); }
+    CameraRays cr;
+    memcpy(cr.eye, cam->eye, 12); memcpy(cr.top_left, cam->top_left, 12); memcpy(cr.du, cam->du, 12); memcpy(cr.dv, cam->dv, 12);
+    const bool fast = (shape->flags & CTC_MATH_FAST) != 0;
+    const int variant = shape_variant(shape);
+    const dim3 grid((width + 15) / 16, (height + 15) / 16);
+#define CALL(F, V) render_kernel<F, V><<<grid, kThreads, 0, ctx->stream>>>(sh, cr, width, height, max_steps, epsilon, d_out)
+    DISPATCH(fast, variant, CALL);
+#undef CALL
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (!out_on_device) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        ctx->async_inflight = true;
+    }
+    return CTC_OK;
+}
+
+int ctc_render(ctc_ctx* ctx, const ctc_shape* shape, const ctc_camera_rays* cam, uint32_t width, uint32_t height,
+               uint32_t max_steps, float epsilon, float* out) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return guarded(ctx, [&] { return render_impl(ctx, shape, cam, width, height, max_steps, epsilon, out, false); });
+}
+
+int ctc_render_device(ctc_ctx* ctx, const ctc_shape* shape, const ctc_camera_rays* cam, uint32_t width, uint32_t height,
+                      uint32_t max_steps, float epsilon, float* d_out) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return guarded(ctx, [&] { return render_impl(ctx, shape, cam, width, height, max_steps, epsilon, d_out, true); });
+}
+
 int ctc_device_alloc(ctc_ctx* ctx, size_t bytes, void** d_ptr) {
     if (!ctx || !d_ptr) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);

@@ -827,6 +827,49 @@ ray_march_kernel(ShapeDev sh, const float* __restrict__ origin, const float* __r
 }
 
 // ---------------------------------------------------------------------------
+// N4: the planned ray-marcher (README.md:12-16) as the same sphere-tracing loop, one thread per PIXEL.
+// Pixel (i, j) looks from `eye` through  top_left + (i + 0.5) du + (j + 0.5) dv ; the ray is marched exactly like
+// a focus ray of get_focii (mesh/mod.rs:229-241).  out[pixel] = (pos.x, pos.y, pos.z, t): the final position and
+// the distance travelled, t < 0 when the ray did not come within `epsilon` of the surface in max_steps steps.
+// The ray set-up is explicit IEEE arithmetic (mul, add, sqrt, div: no contraction), so a host can reproduce the
+// rays bit for bit; the DE follows the shape's math mode.
+// ---------------------------------------------------------------------------
+struct CameraRays { float eye[3], top_left[3], du[3], dv[3]; };
+
+template <bool kFast, int kVariant>
+__global__ void __launch_bounds__(kThreads)
+render_kernel(ShapeDev sh, CameraRays cam, uint32_t width, uint32_t height, uint32_t max_steps, float epsilon,
+              float4* __restrict__ out) {
+    // 16 x 16 pixel tiles per CTA: neighbouring rays take similar step counts
+    const uint32_t tx = threadIdx.x & 15u, ty = threadIdx.x >> 4;
+    const uint32_t i = blockIdx.x * 16u + tx, j = blockIdx.y * 16u + ty;
+    if (i >= width || j >= height) return;
+    const float fi = __fadd_rn((float)i, 0.5f), fj = __fadd_rn((float)j, 0.5f);
+    float d3[3], p3[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float q = __fadd_rn(__fadd_rn(cam.top_left[c], __fmul_rn(fi, cam.du[c])), __fmul_rn(fj, cam.dv[c]));
+        d3[c] = __fsub_rn(q, cam.eye[c]);
+        p3[c] = cam.eye[c];
+    }
+    // cgmath normalize: v * (1 / sqrt((x*x + y*y) + z*z))
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d3[0], d3[0]), __fmul_rn(d3[1], d3[1])), __fmul_rn(d3[2], d3[2]))));
+    const float dx = __fmul_rn(d3[0], inv), dy = __fmul_rn(d3[1], inv), dz = __fmul_rn(d3[2], inv);
+    float px = p3[0], py = p3[1], pz = p3[2], t = 0.0f;
+    bool hit = false;
+    for (uint32_t s = 0; s < max_steps; ++s) {
+        const float d = shape_de<kFast, kVariant>(sh, px, py, pz);
+        px = __fadd_rn(px, __fmul_rn(dx, d));
+        py = __fadd_rn(py, __fmul_rn(dy, d));
+        pz = __fadd_rn(pz, __fmul_rn(dz, d));
+        t = __fadd_rn(t, d);
+        if (d < epsilon) { hit = true; break; }
+        if (!(t < 1e6f)) break;          // the ray has left for good (also ends NaN marches)
+    }
+    out[(size_t)j * width + i] = make_float4(px, py, pz, hit ? t : -1.0f);
+}
+
+// ---------------------------------------------------------------------------
 // Measurement aids (not on the hot path).
 // ---------------------------------------------------------------------------
 // Completed iterations and bail-outs over the sample lattices of a span batch (EXACT arithmetic,

@@ -193,6 +193,26 @@ CTC_API int ctc_mesh_result(ctc_ctx *ctx, uint64_t *n_vertices, uint64_t *n_indi
 
 /* ---- focus rays: ShapeMesh::get_focii's sphere tracing (src/mesh/mod.rs:229-241) ---- */
 
+/* N4: the ray-marcher the reference plans (README.md:12-16, GLSL distance estimator
+ * src/shape/mandelbulb.frag) as one kernel: pixel (i, j), i < width, j < height, looks from `eye` through
+ * top_left + (i + 0.5) du + (j + 0.5) dv and is sphere-traced exactly like a focus ray of ShapeMesh::get_focii
+ * (src/mesh/mod.rs:229-241: pos += dir * d until d < epsilon, at most max_steps steps).  out: width * height
+ * records of four floats, row-major: the final position and the distance travelled, negative when the ray did
+ * not hit.  The ray set-up is plain IEEE f32 arithmetic in a fixed order (normalise = v * (1 / sqrt((x*x+y*y)+z*z)),
+ * as cgmath), so a host can form the same rays bit for bit; with an exact-mode shape a pixel equals ctc_ray_march
+ * on its ray.  ctc_render copies the image to host memory and returns synchronised; ctc_render_device leaves it in
+ * device memory (16-byte aligned), asynchronous on the context's stream. */
+typedef struct ctc_camera_rays {
+    float eye[3];
+    float top_left[3];
+    float du[3];   /* one pixel to the right */
+    float dv[3];   /* one pixel down */
+} ctc_camera_rays;
+CTC_API int ctc_render(ctc_ctx *ctx, const ctc_shape *shape, const ctc_camera_rays *cam, uint32_t width, uint32_t height,
+                       uint32_t max_steps, float epsilon, float *out);
+CTC_API int ctc_render_device(ctc_ctx *ctx, const ctc_shape *shape, const ctc_camera_rays *cam, uint32_t width,
+                              uint32_t height, uint32_t max_steps, float epsilon, float *d_out);
+
 /* DE-bound span culling (not in the reference).  keep[i] = 0 when span i needs no meshing: the
  * distance estimate at its centre (exact arithmetic) exceeds `safety` times the half-diagonal of the skirt-
  * expanded span, i.e. the surface cannot reach it (Shape::min_distance_from is "a lower bound of the distance",

@@ -265,3 +265,47 @@ def test_de_bound_culling_only_drops_spans_the_oracle_finds_empty(oracle, ctx):
     b, _ = cb.generate_for_boxes(tiles, sph, 32, ctx, cull=True)
     assert np.array_equal(a.v_off, b.v_off) and np.array_equal(a.indices, b.indices)
     assert np.array_equal(np.diff(a.v_off.astype(np.int64))[~keep], np.zeros((~keep).sum(), dtype=np.int64))
+
+
+@pytest.mark.gpu
+def test_render_pixels_equal_ray_march_and_the_oracle_loop(oracle, ctx):
+    """ctc_render sphere-traces one ray per pixel with get_focii's loop (mesh/mod.rs:229-241).  In
+    exact mode every pixel must equal ctc_ray_march on the bit-identical ray (formed on the host by pixel_rays), and
+    a sample of pixels must equal the loop run with the CPU oracle's DE."""
+    import cantucci_b200 as cb
+    from cantucci_b200 import _lib
+    W, H = 96, 64
+    shape = cb.Mandelbulb.classic(6, 2.5)
+    cam = cb.look_at_rays((1.6, 1.1, 2.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, W, H)
+    img = cb.render(shape, cam, W, H, 100, 1e-4, ctx)
+    origins, dirs = cb.pixel_rays(cam, W, H)
+    pos = np.empty_like(origins); hit = np.zeros(len(origins), dtype=np.uint32)
+    sh = shape._ctc_shape()
+    ctx.check(_lib.lib().ctc_ray_march(ctx.handle, C.byref(sh), origins.ctypes.data, dirs.ctypes.data, len(origins), 100,
+                                       C.c_float(1e-4), pos.ctypes.data, hit.ctypes.data))
+    flat = img.reshape(-1, 4)
+    got_hit = flat[:, 3] >= 0
+    assert 0.1 < got_hit.mean() < 0.9                                   # the bulb fills part of the frame
+    assert np.array_equal(got_hit, hit.astype(bool))
+    assert np.array_equal(flat[got_hit, :3].view(np.uint32), pos[got_hit].view(np.uint32))
+    # the loop itself with the CPU oracle's DE, on a few pixels (hits and misses)
+    osh = oracle.mandelbulb(8, 6, 2.5)
+    f = np.float32
+    for k in list(np.nonzero(got_hit)[0][::97][:12]) + list(np.nonzero(~got_hit)[0][::211][:4]):
+        p, d = origins[k].copy(), dirs[k]
+        ok, t = False, f(0.0)
+        for _ in range(100):
+            dist = f(oracle.batch_min_distance_from(osh, p.reshape(1, 3))[0])
+            p = (p + (d * dist).astype(np.float32)).astype(np.float32)
+            t = f(t + dist)
+            if dist < f(1e-4):
+                ok = True; break
+            if not (t < f(1e6)):
+                break
+        assert ok == bool(got_hit[k]), k
+        if ok:
+            assert np.array_equal(p.view(np.uint32), flat[k, :3].view(np.uint32)), k
+            assert f(flat[k, 3]).view(np.uint32) == t.view(np.uint32), k
+    # fast mode renders the same silhouette up to a handful of edge pixels
+    fast = cb.render(cb.Mandelbulb.classic(6, 2.5, fast=True), cam, W, H, 100, 1e-4, ctx)
+    assert np.mean((fast[..., 3] >= 0) != (img[..., 3] >= 0)) < 0.01
