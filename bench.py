@@ -237,6 +237,20 @@ def parity_gate(gpu_v, gpu_i, gpu_v_off, gpu_i_off, gpu_planes, ora, spans: np.n
     return out
 
 
+def caller_order(v, i, v_off, i_off, order):
+    """Meshes delivered in the order `order` (table entry k = the caller's span order[k]) re-packed span after span
+    in the caller's order: (v, i, v_off, i_off)."""
+    v_off, i_off = v_off.astype(np.int64), i_off.astype(np.int64)
+    slot = np.empty(len(order), dtype=np.int64)
+    slot[order.astype(np.int64)] = np.arange(len(order))
+    nv, ni = np.diff(v_off)[slot], np.diff(i_off)[slot]
+    vo = np.concatenate([[0], np.cumsum(nv)]).astype(np.uint64)
+    io = np.concatenate([[0], np.cumsum(ni)]).astype(np.uint64)
+    vv = np.concatenate([v[v_off[j]: v_off[j + 1]] for j in slot]) if len(slot) else v[:0]
+    ii = np.concatenate([i[i_off[j]: i_off[j + 1]] for j in slot]) if len(slot) else i[:0]
+    return vv, ii, vo, io
+
+
 def gpu_volume_host(ctx, shape, spans: np.ndarray, vcap: int | None = None, icap: int | None = None):
     """The CUDA path's result in HOST arrays through the public C ABI (ctc_mesh_spans + ctc_sample_signs)."""
     import cantucci_b200 as cb
@@ -330,7 +344,7 @@ def ours_main(args):
         max_span_v = int(probe.v_off[: len(local_spans) + 1].diff().max()) if len(local_spans) else 0
         return nv, ni, max_span_v
 
-    def make_scheduler(spans, shard_mode, gather, wire_packed_from):
+    def make_scheduler(spans, shard_mode, gather, wire_packed_from, surface_first=False):
         """(scheduler, local spans, totals) for one job: `spans` sharded over the ranks, gathered to rank 0."""
         nspans = spans.shape[0]
         mine = shard_indices(nspans, world, rank, shard_mode)
@@ -351,12 +365,13 @@ def ours_main(args):
             dist.all_reduce(caps)
             caps = caps.cpu().numpy()
             sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
-                                        mode=shard_mode, direct=(gather == "direct"), wire_quads=use_packed)
+                                        mode=shard_mode, direct=(gather == "direct"), wire_quads=use_packed,
+                                        surface_first=surface_first and gather == "peer")
         else:
             mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
             sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
         info = {"nspans": nspans, "mine": len(mine), "nv_loc": nv_loc, "ni_loc": ni_loc, "nv_tot": nv_tot, "ni_tot": ni_tot,
-                "packed": bool(use_packed),
+                "packed": bool(use_packed), "surface_first": bool(getattr(sched, "surface_first", False)),
                 "gathered_bytes": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (8 / 6 if use_packed else 4))}
         return sched, local, info
 
@@ -383,7 +398,10 @@ def ours_main(args):
     # ======================================================================== headline: weak scaling ====
     volume = workload_spans(args.tiles)
     spans = volume if world == 1 else np.ascontiguousarray(np.tile(volume, (world, 1)))
-    sched, local_spans, info = make_scheduler(spans, "block", args.gather, wire_packed_from=5)
+    # (N > 4, where rank 0's ingest bounds the gather: the sending ranks mesh their spans surface-first -- the order is
+    # computed inside every step, ctc_order_spans -- so that the bytes travel early and the last launch groups leave no tail)
+    sched, local_spans, info = make_scheduler(spans, "block", args.gather, wire_packed_from=5,
+                                              surface_first=(world > 4 or args.surface_first) and not args.caller_order)
     nspans, total_samples = info["nspans"], info["nspans"] * n3
     step = lambda: run_step(sched, spans, local_spans)
 
@@ -571,8 +589,15 @@ def ours_main(args):
             i_host = torch.empty((pad(info["ni_tot"]),), dtype=torch.int32).pin_memory()
             v_off = np.zeros(nspans + 1, dtype=np.uint64); i_off = np.zeros(nspans + 1, dtype=np.uint64)
 
+            e2e_ordered = not args.caller_order
+            order = np.arange(nspans, dtype=np.uint32)
+
             def e2e_step():
-                ctx.check(L.ctc_mesh_spans(ctx.handle, C.byref(sh), spans.ctypes.data, nspans, RES, v_host.data_ptr(), v_host.shape[0],
+                sp = spans
+                if e2e_ordered:       # plan inside the step: one DE evaluation per span, then mesh surface-first
+                    ctx.check(L.ctc_order_spans(ctx.handle, C.byref(sh), spans.ctypes.data, nspans, RES, order.ctypes.data))
+                    sp = np.take(spans, order, axis=0)
+                ctx.check(L.ctc_mesh_spans(ctx.handle, C.byref(sh), sp.ctypes.data, nspans, RES, v_host.data_ptr(), v_host.shape[0],
                                            i_host.data_ptr(), i_host.shape[0], v_off.ctypes.data, i_off.ctypes.data, None))
             for _ in range(3):
                 e2e_step()
@@ -588,15 +613,42 @@ def ours_main(args):
             nv, ni = int(v_off[nspans]), int(i_off[nspans])
             e2e = {"value": total_samples / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(nspans * 48),
                    "d2h_bytes_per_step": int(nv * 28 + (ni // 6 * 8 if packed_wire else ni * 4) + 2 * (nspans + 1) * 8 + 48),
-                   "api": "ctc_mesh_spans (host pointers; pinned host buffers)", "steps": args.steps,
+                   "api": ("ctc_order_spans + ctc_mesh_spans" if e2e_ordered else "ctc_mesh_spans") + " (host pointers; pinned host buffers)",
+                   "span_order": ("surface-first: planned inside every step by ctc_order_spans (one DE evaluation per span), the copy "
+                                  "pipeline starts with the first launch group") if e2e_ordered else "caller order",
+                   "steps": args.steps,
                    "index_wire": (f"packed 8-byte quad records over PCIe, widened into the caller's u32 index buffer by {wire1[2]} host threads "
                                   "inside the call (the caller receives six u32 per quad)") if packed_wire else "six u32 per quad"}
+            # ---- the same step with the upload step removed: meshes land in interop buffers the renderer
+            # imports by file descriptor; the only device->host bytes are the two offset tables -----------------------
+            e2e["interop"] = None
+            try:
+                vb, ib = cb.InteropBuffer(ctx, pad(nv) * 28), cb.InteropBuffer(ctx, pad(ni) * 4)
+                for _ in range(3):
+                    views, _t = cb.generate_views(spans, shape, RES, ctx, vb, ib)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    views, _t = cb.generate_views(spans, shape, RES, ctx, vb, ib)
+                dti = (time.perf_counter() - t0) / args.steps
+                e2e["interop"] = {"value": total_samples / dti, "unit": UNIT, "ms_per_step": dti * 1e3,
+                                  "d2h_bytes_per_step": int(2 * (nspans + 1) * 8), "h2d_bytes_per_step": int(nspans * 24),
+                                  "same_tables": bool(int(views.v_off[-1]) == nv and int(views.i_off[-1]) == ni),
+                                  "api": "generate_views: ctc_mesh_spans_device into ctc_interop_alloc buffers (exported as POSIX file "
+                                         "descriptors for VkImportMemoryFdInfoKHR), ctc_mesh_result, offset tables read back; not the headline: "
+                                         "the reference's wgpu 0.6 cannot import external memory"}
+                vb.close(); ib.close()
+            except Exception as ex:          # (a driver without the VMM export: reported, not fatal)
+                e2e["interop"] = {"error": str(ex)[:200]}
             # ---- parity gate + CPU baseline: ONE oracle run over the whole volume serves both -----------------
             if not args.no_cpu:
                 ora = oracle_volume(spans)
                 planes = cb.sample_signs(spans, shape, RES, ctx)
                 gv = v_host.numpy().view(np.uint8).reshape(-1)[: nv * 28].view(cb.VERTEX_DTYPE)
-                parity = parity_gate(gv, i_host.numpy().view(np.uint32)[:ni], v_off, i_off, planes, ora, spans, exact=not fast)
+                gi = i_host.numpy().view(np.uint32)[:ni]
+                gv_off, gi_off = v_off, i_off
+                if e2e_ordered:       # back to the caller's span order: the gate (and its SHA-256) are order-independent this way
+                    gv, gi, gv_off, gi_off = caller_order(gv, gi, v_off, i_off, order)
+                parity = parity_gate(gv, gi, gv_off, gi_off, planes, ora, spans, exact=not fast)
                 parity["mode"] = "fast" if fast else "exact"
                 parity["checked"] = "the e2e leg's host buffers (ctc_mesh_spans) and ctc_sample_signs against the CPU oracle, all spans"
                 cpu = {"value": ora["samples"] / ora["secs"], "unit": UNIT, "cores": ora["threads"], "kind": "port",
@@ -616,7 +668,9 @@ def ours_main(args):
                         "parallelism": (f"{world} volume(s) of {info['mine']} spans, one per rank (weak scaling), meshes gathered to rank 0"
                                         + ("" if world == 1 else (" by one-sided puts into rank 0's IPC-mapped buffers (copy engines over "
                                            "NVLink, pipelined behind compute)" if args.gather == "peer" else " by grouped NCCL send/recv"))),
-                        "index_wire": "packed 8-byte quads, widened on rank 0" if info["packed"] else "six u32 per quad"},
+                        "index_wire": "packed 8-byte quads, widened on rank 0" if info["packed"] else "six u32 per quad",
+                        "span_order": ("senders mesh surface-first (ctc_order_spans inside every step; rank 0 maps the tables back to the "
+                                       "caller's span order)") if info["surface_first"] else "caller order"},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
             "vertices": info["nv_tot"], "indices": info["ni_tot"], "gathered_bytes_per_step": info["gathered_bytes"],
             "gpu_launches": int(launches2 - launches1),
@@ -761,6 +815,8 @@ def main():
     ap.add_argument("--strong-steps", type=int, default=3, help="timed steps of the strong-scaling leg")
     ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
     ap.add_argument("--wire-packed", action="store_true", help="N>1: force packed quad records (default only for N > 4)")
+    ap.add_argument("--caller-order", action="store_true", help="never re-order spans (e2e leg, senders of the N > 4 gather)")
+    ap.add_argument("--surface-first", action="store_true", help="N>1: senders mesh surface-first at every N (default only for N > 4)")
     ap.add_argument("--wire-u32", action="store_true",
                     help="N>1, --gather peer: ship six u32 indices per quad instead of packed 8-byte quad records")
     ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],

@@ -73,6 +73,7 @@ EXPORTS = (
     "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats", "ctc_ctx_set_host_index_wire", "ctc_ctx_host_index_wire_stats", "ctc_ctx_set_wire_progress", "ctc_cull_spans", "ctc_expand_quads_host", "ctc_render", "ctc_render_device",
     "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
     "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
+    "ctc_interop_alloc", "ctc_interop_import", "ctc_interop_free", "ctc_device_read", "ctc_device_write", "ctc_order_spans",
 )
 
 _lib = None
@@ -145,6 +146,18 @@ def lib() -> C.CDLL:
     L.ctc_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.ctc_ipc_close.restype = C.c_int
     L.ctc_ipc_close.argtypes = [vp, vp]
+    L.ctc_interop_alloc.restype = C.c_int
+    L.ctc_interop_alloc.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(sz)]
+    L.ctc_interop_import.restype = C.c_int
+    L.ctc_interop_import.argtypes = [vp, C.c_int, sz, C.POINTER(vp)]
+    L.ctc_interop_free.restype = C.c_int
+    L.ctc_interop_free.argtypes = [vp, vp]
+    L.ctc_order_spans.restype = C.c_int
+    L.ctc_order_spans.argtypes = [vp, shp, spn, sz, u32, vp]
+    L.ctc_device_write.restype = C.c_int
+    L.ctc_device_write.argtypes = [vp, vp, vp, sz]
+    L.ctc_device_read.restype = C.c_int
+    L.ctc_device_read.argtypes = [vp, vp, vp, sz]
     L.ctc_ctx_set_index_wire.restype = C.c_int
     L.ctc_ctx_set_index_wire.argtypes = [vp, C.c_int]
     L.ctc_expand_quads.restype = C.c_int

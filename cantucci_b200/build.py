@@ -12,6 +12,8 @@ SOURCES = [os.path.join(CSRC, "cantucci_b200.cu")]
 DEPS = SOURCES + [
     os.path.join(CSRC, "kernels.cuh"),
     os.path.join(CSRC, "de_device.cuh"),
+    os.path.join(CSRC, "multi.inc"),
+    os.path.join(CSRC, "interop.inc"),
     os.path.join(HERE, "..", "include", "cantucci_b200.h"),
 ]
 

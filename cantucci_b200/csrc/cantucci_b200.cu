@@ -10,11 +10,13 @@
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
 #endif
+#include <chrono>
 #include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -263,7 +265,7 @@ struct ctc_ctx {
     DevBuf geom, grids, sign_bits, m_active, word_vpre, cell_of, quad_of, span_first, neg8, chunk_cnt, span_tot, span_pre, state;
     DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
     DevBuf pts_in, pts_out;
-    PinnedBuf h_geom, h_state, h_tables;
+    PinnedBuf h_geom, h_state, h_tables, h_pts;
 
     // extraction (passes 2-3) runs on its own stream so that group g's small, latency-bound kernels
     // overlap group g+1's DE kernel; grids and sign planes are double-buffered for that
@@ -283,7 +285,12 @@ struct ctc_ctx {
     size_t ev_used = 0;
     std::vector<EventPair> ev_pairs;
     bool mesh_pending = false;
+
+    // interop buffers of this context (interop.inc): base address -> mapped size
+    std::map<void*, size_t> interop;
 };
+
+void interop_release_all(ctc_ctx* c);     // interop.inc
 
 namespace {
 
@@ -860,8 +867,9 @@ void ctc_ctx_destroy(ctc_ctx* c) {
                       &c->span_first, &c->neg8, &c->chunk_cnt, &c->span_tot, &c->span_pre, &c->state, &c->out_v, &c->out_idx,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
+    interop_release_all(c);
     c->expander.stop();
-    c->h_geom.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release(); c->h_wire.release(); c->h_vstage.release(); c->h_wire_prog.release();
+    c->h_geom.release(); c->h_pts.release(); c->h_state.release(); c->h_tables.release(); c->b_v.release(); c->b_i.release(); c->h_wire.release(); c->h_vstage.release(); c->h_wire_prog.release();
     for (cudaEvent_t e : c->wire_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->group_events) cudaEventDestroy(e);
@@ -1063,6 +1071,11 @@ int ctc_mesh_result(ctc_ctx* ctx, uint64_t* n_vertices, uint64_t* n_indices, ctc
 static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
                                 ctc_vertex* v, size_t vcap, uint32_t* idx, size_t icap, uint64_t* v_off, uint64_t* i_off,
                                 ctc_timings* timings, bool host_wire) {
+    // CANTUCCI_B200_TRACE=1: one stderr line per call with the host-side milestones of the copy pipeline (ms)
+    static const bool trace = getenv("CANTUCCI_B200_TRACE") != nullptr;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
+    double t_enq = 0, t_first = 0, t_groups = 0, t_widen = 0, t_copies = 0;
     CK(cudaSetDevice(ctx->device));
     CK(ctx->out_v.ensure((vcap ? vcap : 1) * sizeof(ctc_vertex)));
     CK(ctx->out_idx.ensure((icap ? icap : 1) * sizeof(uint32_t)));
@@ -1090,6 +1103,7 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
                              ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
                              /*pipeline=*/true, packed);
     if (rc) return rc;
+    if (trace) t_enq = since();
     // Everything is enqueued.  The offset tables follow the kernels on the compute stream (straight
     // to the destination when it is device/peer memory, through a pinned staging buffer when it is
     // host memory, so the call never blocks on a pageable copy); each group's slice of the mesh is
@@ -1130,6 +1144,7 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
     int copy_rc = CTC_OK;
     for (size_t g = 0; g < ctx->n_groups && copy_rc == CTC_OK; ++g) {
         cudaError_t e = cudaEventSynchronize(ctx->group_events[g]);
+        if (trace && g == 0) t_first = since();
         const unsigned long long tv = ctx->progress_h[2 * g], ti = 6ull * ctx->progress_h[2 * g + 1];
         const size_t cv = tv < vcap ? (size_t)tv : vcap, ci = ti < icap ? (size_t)ti : icap;
         if (e == cudaSuccess && cv > done_v) {
@@ -1179,12 +1194,19 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
         if (cudaMemcpyAsync(ctx->wire_progress, wprog + ctx->n_groups, 8, cudaMemcpyDefault, ctx->copy_stream2) != cudaSuccess)
             copy_rc = fail_cuda(ctx, cudaGetLastError(), "wire progress");
     }
+    if (trace) t_groups = since();
     if (workers) ctx->expander.finish();         // (always: the workers must be idle before the landing buffers are reused)
+    if (trace) t_widen = since();
     if (copy_rc != CTC_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2); return copy_rc; }
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream2));
+    if (trace) t_copies = since();
     uint64_t nv = 0, ni = 0;
     const int status = mesh_result_impl(ctx, &nv, &ni, timings, /*state_already_copied=*/true);   // syncs the compute stream
+    if (trace)
+        fprintf(stderr, "[ctc trace] %zu spans, %zu groups: enqueued %.2f, first group %.2f, last group %.2f, host threads done %.2f, "
+                        "copies done %.2f, end %.2f ms (host wire %d)\n", nspans, ctx->n_groups, t_enq, t_first, t_groups, t_widen,
+                t_copies, since(), (int)host_wire);
     if (status != CTC_ERR_CUDA && !tables_on_device) {
         memcpy(v_off, ctx->h_tables.p, tbytes);
         memcpy(i_off, static_cast<char*>(ctx->h_tables.p) + tbytes, tbytes);
@@ -1361,6 +1383,45 @@ int ctc_ctx_coalescing_stats(ctc_ctx* ctx, uint64_t* batches, uint64_t* requests
     return CTC_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// DE at every span's centre (exact arithmetic) and the span's reach = half-diagonal of its skirt-expanded box
+// (buffer.rs:64-67): what span culling and the surface-first order are computed from.  Through a pinned buffer, one
+// kernel, one synchronisation.  d and reach point into ctx->h_pts.
+int centre_distances(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                     const float** d_out, const float** reach_out) {
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->h_pts.ensure(nspans * 20));
+    float* centres = static_cast<float*>(ctx->h_pts.p);
+    float* d = centres + 3 * nspans;
+    float* reach = d + nspans;
+    for (size_t i = 0; i < nspans; ++i) {
+        double r2 = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            const double ext = (double)spans[i].end[c] - (double)spans[i].start[c];
+            const double half = 0.5 * ext + ext / (double)resolution;       // half extent + the one-cell skirt (buffer.rs:64-67)
+            centres[3 * i + c] = (float)(0.5 * ((double)spans[i].start[c] + (double)spans[i].end[c]));
+            r2 += half * half;
+        }
+        reach[i] = (float)(std::sqrt(r2) * 1.0001);           // (rounding of the centre and of the sample positions)
+    }
+    ctc_shape exact = *shape;
+    exact.flags &= ~(uint32_t)CTC_MATH_FAST;
+    CK(ctx->pts_in.ensure(nspans * 12)); CK(ctx->pts_out.ensure(nspans * 4));
+    CK(cudaMemcpyAsync(ctx->pts_in.p, centres, nspans * 12, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = de_batch_impl(ctx, &exact, ctx->pts_in.as<float>(), nspans, ctx->pts_out.as<float>()); if (rc) return rc;
+    CK(cudaMemcpyAsync(d, ctx->pts_out.p, nspans * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *d_out = d; *reach_out = reach;
+    return CTC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 // DE-bound span culling.  The distance estimate at a span's centre bounds how close the surface can
 // be (Shape::min_distance_from, shape/mod.rs:26-37: "a lower bound of the distance"); a span whose skirt-expanded
 // box lies inside that ball has an all-positive sample grid and an empty mesh.  Shapes with an upper bound as well
@@ -1376,31 +1437,56 @@ int ctc_cull_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, 
         if (nspans == 0) return CTC_OK;
         if (!keep) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "keep is NULL");
         if (!(safety >= 1.0f)) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "safety must be >= 1");
-        CK(cudaSetDevice(ctx->device));
-        std::vector<float> centres(3 * nspans), reach(nspans), d(nspans);
-        for (size_t i = 0; i < nspans; ++i) {
-            double r2 = 0.0;
-            for (int c = 0; c < 3; ++c) {
-                const double ext = (double)spans[i].end[c] - (double)spans[i].start[c];
-                const double half = 0.5 * ext + ext / (double)resolution;       // half extent + the one-cell skirt (buffer.rs:64-67)
-                centres[3 * i + c] = (float)(0.5 * ((double)spans[i].start[c] + (double)spans[i].end[c]));
-                r2 += half * half;
-            }
-            reach[i] = (float)(std::sqrt(r2) * 1.0001);       // (rounding of the centre and of the sample positions)
-        }
-        ctc_shape exact = *shape;
-        exact.flags &= ~(uint32_t)CTC_MATH_FAST;
-        CK(ctx->pts_in.ensure(nspans * 12)); CK(ctx->pts_out.ensure(nspans * 4));
-        CK(cudaMemcpyAsync(ctx->pts_in.p, centres.data(), nspans * 12, cudaMemcpyHostToDevice, ctx->stream));
-        rc = de_batch_impl(ctx, &exact, ctx->pts_in.as<float>(), nspans, ctx->pts_out.as<float>()); if (rc) return rc;
-        CK(cudaMemcpyAsync(d.data(), ctx->pts_out.p, nspans * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        const float *d, *reach;
+        rc = centre_distances(ctx, shape, spans, nspans, resolution, &d, &reach); if (rc) return rc;
         const bool two_sided = shape->kind == CTC_SHAPE_SPHERE;         // max_distance_from is Some(..) (sphere.rs:37)
         for (size_t i = 0; i < nspans; ++i) {
             const bool outside = d[i] > safety * reach[i];
             const bool inside = two_sided && -d[i] > reach[i];
             keep[i] = (outside || inside) ? 0 : 1;                       // (NaN compares false: kept)
         }
+        return CTC_OK;
+    });
+}
+
+// Cost-aware span order ("surface spans are 10-50x more expensive than empty ones").  order[k] = index of
+// the span to mesh k-th: ascending |DE(centre)| / reach, i.e. the spans most likely to hold surface first and the
+// provably empty ones last (stable: equal keys keep the caller's order; NaN counts as 0).  A call made in this order
+// produces its mesh bytes EARLY, so the copy pipeline behind the launch groups (device->host over PCIe, or the puts
+// of the multi-GPU gather over NVLink) is busy from the first group on and the groups computed last -- empty space --
+// leave nothing to copy after the kernels end.  The meshes themselves do not depend on the order.
+int ctc_order_spans(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t resolution,
+                    uint32_t* order) {
+    if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return guarded(ctx, [&]() -> int {
+        ShapeDev sh; uint32_t lg;
+        int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
+        rc = check_spans(ctx, spans, nspans, resolution, &lg); if (rc) return rc;
+        if (nspans == 0) return CTC_OK;
+        if (!order) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "order is NULL");
+        if (nspans > 0xFFFFFFFFull) return fail(ctx, CTC_ERR_INVALID_ARGUMENT, "more than 2^32 - 1 spans");
+        const float *d, *reach;
+        rc = centre_distances(ctx, shape, spans, nspans, resolution, &d, &reach); if (rc) return rc;
+        // keys are non-negative floats: their bit patterns sort like unsigned integers (LSD radix sort, 3 x 11 bits)
+        std::vector<uint32_t> key(nspans), tmp_key(nspans), tmp_idx(nspans);
+        for (size_t i = 0; i < nspans; ++i) {
+            float k = std::fabs(d[i]) / reach[i];
+            if (!(k == k)) k = 0.0f;
+            memcpy(&key[i], &k, 4);
+            order[i] = (uint32_t)i;
+        }
+        uint32_t* ka = key.data(); uint32_t* kb = tmp_key.data();
+        uint32_t* ia = order;      uint32_t* ib = tmp_idx.data();
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = 11 * pass;
+            size_t hist[2049] = {0};
+            for (size_t i = 0; i < nspans; ++i) hist[((ka[i] >> shift) & 2047u) + 1]++;
+            for (int b = 0; b < 2048; ++b) hist[b + 1] += hist[b];
+            for (size_t i = 0; i < nspans; ++i) { const size_t at = hist[(ka[i] >> shift) & 2047u]++; kb[at] = ka[i]; ib[at] = ia[i]; }
+            std::swap(ka, kb); std::swap(ia, ib);
+        }
+        if (ia != order) memcpy(order, ia, nspans * sizeof(uint32_t));    // (three passes: the result sits in the scratch array)
         return CTC_OK;
     });
 }
@@ -1733,3 +1819,4 @@ int ctc_fp32_peak_probe(ctc_ctx* ctx, double* tflops, int* num_sms) {
 }  // extern "C"
 
 #include "multi.inc"
+#include "interop.inc"

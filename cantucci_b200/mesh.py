@@ -52,11 +52,14 @@ class MeshBatch:
     indices: np.ndarray
     v_off: np.ndarray        # u64 [nspans+1]
     i_off: np.ndarray        # u64 [nspans+1]
+    slot: np.ndarray | None = None   # meshed in another order than the caller's: slot[k] = place of span k in the tables
 
     def __len__(self) -> int:
         return len(self.v_off) - 1
 
     def mesh(self, k: int) -> MeshBuffer:
+        if self.slot is not None:
+            k = int(self.slot[k])
         return MeshBuffer(self.vertices[int(self.v_off[k]):int(self.v_off[k + 1])],
                           self.indices[int(self.i_off[k]):int(self.i_off[k + 1])])
 
@@ -111,19 +114,41 @@ def cull_spans(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = 
     return keep.astype(bool)
 
 
+def order_spans(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = None) -> np.ndarray:
+    """Cost-aware span order (ctc_order_spans): indices of the spans, the ones most likely to hold surface first
+    (ascending |DE(centre)| / half-diagonal), the provably empty ones last.  Meshing in this order keeps the copy
+    pipeline behind the launch groups busy from the start and leaves no copy tail.  Not part of the reference, whose
+    thread pool takes the jobs in tree order (mesh/mod.rs:129-161); never applied implicitly."""
+    ctx = ctx or _lib.default_context()
+    arr = spans_array(spans)
+    _check_args(arr, resolution)
+    order = np.zeros(arr.shape[0], dtype=np.uint32)
+    sh = shape._ctc_shape()
+    ctx.check(_lib.lib().ctc_order_spans(ctx.handle, C.byref(sh), arr.ctypes.data, arr.shape[0], resolution, order.ctypes.data))
+    return order.astype(np.int64)
+
+
 def generate_for_boxes(spans, shape: Shape, resolution: int, ctx: _lib.Context | None = None,
                        vcap: int | None = None, icap: int | None = None, out_v: np.ndarray | None = None,
-                       out_i: np.ndarray | None = None, cull: bool = False):
+                       out_i: np.ndarray | None = None, cull: bool = False, surface_first: bool = False):
     """generate_for_box for every span in ONE batched call -> (MeshBatch, Timings).
 
     Output capacity is guessed from the resolution and retried with the exact
     required size when the library reports CTC_ERR_OVERFLOW.  A lerp-factor
     failure raises AssertionError like the reference's panic (math.rs:19).
     cull = True (not in the reference): spans the DE bound proves empty (cull_spans) are not meshed at all;
-    they come back as empty meshes."""
+    they come back as empty meshes.
+    surface_first = True (not in the reference): the spans are meshed in order_spans' order; `mesh(k)` still is the
+    mesh of the caller's k-th span (MeshBatch.slot maps it to its place in the buffers)."""
     ctx = ctx or _lib.default_context()
     arr = spans_array(spans)
     _check_args(arr, resolution)
+    if surface_first and arr.shape[0] > 1:
+        order = order_spans(arr, shape, resolution, ctx)
+        sub, t = generate_for_boxes(np.ascontiguousarray(arr[order]), shape, resolution, ctx, vcap, icap, out_v, out_i, cull)
+        slot = np.empty_like(order)
+        slot[order] = np.arange(order.shape[0])
+        return MeshBatch(sub.vertices, sub.indices, sub.v_off, sub.i_off, slot), t
     if cull and arr.shape[0]:
         keep = cull_spans(arr, shape, resolution, ctx)
         if not keep.all():

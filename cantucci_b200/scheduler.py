@@ -31,6 +31,14 @@ def shard_indices(nspans: int, world: int, rank: int, mode: str = "interleave") 
     return np.arange(rank, nspans, world, dtype=np.int64)
 
 
+def plan_order(ctx, shape_struct, local: np.ndarray, resolution: int) -> np.ndarray:
+    """ctc_order_spans over a rank's spans: int64 indices, surface-first."""
+    order = np.zeros(local.shape[0], dtype=np.uint32)
+    ctx.check(_lib.lib().ctc_order_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
+                                         order.ctypes.data))
+    return order.astype(np.int64)
+
+
 def agree_on_status(dist, torch, device, world: int, rc: int) -> int:
     """Every rank learns the worst status of the step BEFORE any rank raises: a data-dependent failure on one
     rank (CTC_ERR_LERP_ASSERT, CTC_ERR_OVERFLOW) must not leave the others waiting in a barrier / all-gather."""
@@ -221,8 +229,13 @@ class PeerGatherScheduler:
 
     def __init__(self, dist, torch, ctx: _lib.Context, rank: int, world: int, device, nspans: int,
                  caps_v: list, caps_i: list, mode: str = "interleave", direct: bool = False,
-                 wire_quads: bool = False):
-        """wire_quads = True (copy-engine mode only): ranks > 0 ship one packed 8-byte record per quad
+                 wire_quads: bool = False, surface_first: bool = False):
+        """surface_first = True: every SENDING rank meshes its spans in ctc_order_spans' order (the spans most likely
+        to hold surface first, provably empty ones last), so its puts start with the first launch group and the
+        groups computed last leave nothing in flight when the kernels end -- rank 0's ingest is the bound of the
+        gather at 8 GPUs, and what it cannot hide is the tail.  The order is computed inside every step and travels
+        with the offset tables; the per-span ranges rank 0 assembles are in the caller's span order as before.
+        wire_quads = True (copy-engine mode only): ranks > 0 ship one packed 8-byte record per quad
         instead of six u32 indices (a third of the index bytes, -31 % of the whole gather) into a wire
         buffer on rank 0, which widens them into the gathered index buffer after the barrier.
         direct = False: ranks > 0 mesh into local buffers and the copy engines put each launch group's
@@ -231,6 +244,7 @@ class PeerGatherScheduler:
         self.dist, self.torch, self.ctx, self.rank, self.world, self.device = dist, torch, ctx, rank, world, device
         self.nspans, self.mode, self.direct = nspans, mode, direct
         self.wire_quads = bool(wire_quads) and not direct and world > 1
+        self.surface_first = bool(surface_first) and world > 1
         self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
         self.n_r = [len(x) for x in self.shards]
         # regions start on 256-byte boundaries (the kernels store 8-byte index pairs)
@@ -241,7 +255,8 @@ class PeerGatherScheduler:
         self.base_t = np.concatenate([[0], np.cumsum([n + 1 for n in self.n_r])]).astype(np.int64)   # table entries
         L = _lib.lib()
         # one table buffer: all v_off tables, then all i_off tables (a single small D2H per step on rank 0)
-        sizes = [int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, 2 * int(self.base_t[-1]) * 8]
+        # (surface_first: a third table section carries the order every rank meshed its spans in)
+        sizes = [int(self.base_v[-1]) * 28, int(self.base_i[-1]) * 4, (3 if self.surface_first else 2) * int(self.base_t[-1]) * 8]
         if self.wire_quads:
             sizes.append(int(self.base_i[-1]) // 6 * 8 + 64)      # packed quad records of every rank, at quad offsets
             sizes.append(world * 8)                               # one progress word per rank (ctc_ctx_set_wire_progress)
@@ -311,6 +326,13 @@ class PeerGatherScheduler:
             local = np.ascontiguousarray(spans[self.shards[rank]])
         pv, pi, tv, ti = self._region(rank)
         self._epoch += 1
+        if self.surface_first and local.shape[0]:
+            # rank 0's own meshes do not travel: it keeps the caller's order (identity in its table section)
+            order = plan_order(ctx, shape_struct, local, resolution) if rank != 0 else np.arange(local.shape[0], dtype=np.int64)
+            if rank != 0:
+                local = np.ascontiguousarray(local[order])
+            ctx.check(L.ctc_device_write(ctx.handle, self.ptrs[2].value + (2 * int(self.base_t[-1]) + int(self.base_t[rank])) * 8,
+                                         order.ctypes.data, order.nbytes))
         if rank == 0 or self.direct:
             ctx.check(L.ctc_mesh_spans_device(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0],
                                               resolution, pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti))
@@ -382,12 +404,14 @@ class LazyGather:
         if self._built is None:
             s = self._s
             nt = int(s.base_t[-1])
-            tv_h, ti_h = self._tables[:nt], self._tables[nt:]
+            tv_h, ti_h = self._tables[:nt], self._tables[nt: 2 * nt]
             span_v = np.zeros((s.nspans, 2), dtype=np.int64)
             span_i = np.zeros((s.nspans, 2), dtype=np.int64)
             nv = ni = 0
             for r in range(s.world):
                 idx = s.shards[r]
+                if s.surface_first:      # rank r meshed its spans in this order: table entry k belongs to span idx[order[k]]
+                    idx = idx[self._tables[2 * nt + s.base_t[r]: 2 * nt + s.base_t[r] + len(idx)]]
                 ov = tv_h[s.base_t[r]: s.base_t[r + 1]]
                 oi = ti_h[s.base_t[r]: s.base_t[r + 1]]
                 span_v[idx, 0], span_v[idx, 1] = s.base_v[r] + ov[:-1], s.base_v[r] + ov[1:]

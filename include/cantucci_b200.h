@@ -222,6 +222,14 @@ CTC_API int ctc_render_device(ctc_ctx *ctx, const ctc_shape *shape, const ctc_ca
  * configs against the CPU oracle.  Culling is never applied implicitly by the mesh calls. */
 CTC_API int ctc_cull_spans(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
                            uint32_t resolution, float safety, uint8_t *keep);
+/* Cost-aware span order: order[k] = index of the span to mesh k-th, ascending |DE(centre)| / reach --
+ * the spans most likely to hold surface first, the provably empty ones last (stable; NaN counts as 0).  A mesh
+ * call made in this order produces its bytes early, so the copy pipeline behind the launch groups (PCIe to the
+ * host, or the NVLink puts of the multi-GPU gather) is busy from the first group on and the groups computed last
+ * leave nothing to copy after the kernels end.  The meshes do not depend on the order.  Host pointers; synchronous
+ * (one DE evaluation per span). */
+CTC_API int ctc_order_spans(ctc_ctx *ctx, const ctc_shape *shape, const ctc_span *spans, size_t nspans,
+                            uint32_t resolution, uint32_t *order);
 
 /* n rays (origin, unit direction; packed xyz, HOST pointers).  Each ray repeats
  * `d = DE(pos); pos += dir * d; if d < epsilon { hit }` up to max_steps times
@@ -284,6 +292,29 @@ CTC_API int ctc_device_free(ctc_ctx *ctx, void *d_ptr);
 CTC_API int ctc_ipc_export(ctc_ctx *ctx, const void *d_ptr, unsigned char handle[64]);
 CTC_API int ctc_ipc_open(ctc_ctx *ctx, const unsigned char handle[64], void **d_ptr);
 CTC_API int ctc_ipc_close(ctc_ctx *ctx, void *d_ptr);
+
+/* ---- interop buffers: the upload step after the path ------- */
+
+/* Replaces the host round trip of `MeshView::new` (src/mesh/view.rs:23-41: `create_buffer_init` from
+ * `bytemuck::cast_slice(vertices)` / `(indices)`, i.e. host memory -> Vulkan buffer).  An interop buffer is
+ * device memory of the context's GPU with a POSIX file-descriptor handle (CUDA virtual memory management):
+ * the renderer imports `fd` as VkDeviceMemory (VkImportMemoryFdInfoKHR, OPAQUE_FD, VK_KHR_external_memory_fd;
+ * allocationSize = *allocated_bytes) and binds its vertex / index VkBuffers to it; ctc_mesh_spans_device,
+ * ctc_mesh_spans_multi_device and ctc_render_device take `*d_ptr` like any device pointer, so the meshes are
+ * written straight into the memory the draw calls read -- no PCIe bytes but the per-span offset tables.
+ * Hand-over: ctc_ctx_synchronize (or the stream's own event) before the renderer's submit.
+ * The caller owns `fd` (close(2) it after the import; the memory lives while any mapping or import does).
+ * ctc_interop_import maps such a descriptor in another context or process (CUDA consumer, tests).
+ * ctc_interop_free unmaps a buffer obtained from either call; ctc_ctx_destroy frees what is left. */
+CTC_API int ctc_interop_alloc(ctc_ctx *ctx, size_t bytes, void **d_ptr, int *fd, size_t *allocated_bytes);
+CTC_API int ctc_interop_import(ctc_ctx *ctx, int fd, size_t allocated_bytes, void **d_ptr);
+CTC_API int ctc_interop_free(ctc_ctx *ctx, void *d_ptr);
+/* Synchronous read of device memory (interop or not) into host memory, ordered behind the context's stream:
+ * the offset tables of a ctc_mesh_spans_device call, or a look at an imported buffer. */
+CTC_API int ctc_device_read(ctc_ctx *ctx, void *host_dst, const void *d_src, size_t bytes);
+/* The other direction (the destination may be a mapped peer buffer, ctc_ipc_open): small host-side tables that
+ * travel with a gathered result, e.g. the order a rank meshed its spans in (ctc_order_spans). */
+CTC_API int ctc_device_write(ctc_ctx *ctx, void *d_dst, const void *host_src, size_t bytes);
 
 /* Index wire format of ctc_mesh_spans (the host / peer destination variant only).  0 (default): six
  * u32 indices per quad, the reference's layout.  1: one packed 8-byte record per quad (four 16-bit

@@ -49,6 +49,8 @@ direct = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), 
                              direct=True)
 packed = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
                              wire_quads=True)
+ordered = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
+                              wire_quads=True, surface_first=True)
 host = HostGatherScheduler(dist, ctx, rank, world, len(spans), [cap_v] * world, [cap_i] * world)
 for _ in range(2):
     g1 = nccl.run(sh, spans, R)
@@ -56,6 +58,7 @@ for _ in range(2):
     g3 = direct.run(sh, spans, R)
     g4 = host.run(sh, spans, R)
     g5 = packed.run(sh, spans, R)
+    g6 = ordered.run(sh, spans, R)
     torch.cuda.synchronize()
 if rank == 0:
     check(g1, "nccl")
@@ -63,10 +66,12 @@ if rank == 0:
     check(g3, "direct")
     check(g4, "host")
     check(g5, "packed quads")
+    check(g6, "packed quads, senders mesh surface-first")
     print("MULTIGPU_PARITY_OK", world, g2.n_vertices, g2.n_indices, flush=True)
 dist.barrier()
 peer.close()
 direct.close()
 host.close()
 packed.close()
+ordered.close()
 dist.destroy_process_group()

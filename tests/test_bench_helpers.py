@@ -54,3 +54,20 @@ def test_clock_sampler_summarises_rows_inside_the_timed_region():
     out = s.stop()
     assert out["samples"] == 2 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
     assert out["sm_mhz"] == 1932.5
+
+
+def test_caller_order_repacks_the_delivered_meshes():
+    """bench.caller_order: meshes delivered surface-first (table entry k = the caller's span order[k]) re-packed span
+    after span in the caller's order, so that the parity gate and its SHA-256 do not depend on the order."""
+    rng = np.random.default_rng(0)
+    n = 50
+    cnt = rng.integers(0, 5, n)
+    order = rng.permutation(n).astype(np.uint32)
+    v_off = np.concatenate([[0], np.cumsum(cnt[order])]).astype(np.uint64)
+    i_off = (6 * v_off).astype(np.uint64)
+    v = np.concatenate([np.full(cnt[s], s) for s in order]).astype(np.int32)
+    i = np.repeat(v, 6)
+    vv, ii, vo, io = bench.caller_order(v, i, v_off, i_off, order)
+    assert np.array_equal(vv, np.concatenate([np.full(cnt[s], s) for s in range(n)]))
+    assert np.array_equal(ii, np.repeat(vv, 6))
+    assert np.array_equal(np.diff(vo.astype(np.int64)), cnt) and np.array_equal(io, 6 * vo)
