@@ -235,6 +235,8 @@ class PeerGatherScheduler:
         groups computed last leave nothing in flight when the kernels end -- rank 0's ingest is the bound of the
         gather at 8 GPUs, and what it cannot hide is the tail.  The order is computed inside every step and travels
         with the offset tables; the per-span ranges rank 0 assembles are in the caller's span order as before.
+        (A context reports its packed-wire progress to the words of ONE scheduler: give every wire_quads scheduler of
+        a process its own Context.)
         wire_quads = True (copy-engine mode only): ranks > 0 ship one packed 8-byte record per quad
         instead of six u32 indices (a third of the index bytes, -31 % of the whole gather) into a wire
         buffer on rank 0, which widens them into the gathered index buffer after the barrier.
@@ -410,7 +412,7 @@ class LazyGather:
             nv = ni = 0
             for r in range(s.world):
                 idx = s.shards[r]
-                if s.surface_first:      # rank r meshed its spans in this order: table entry k belongs to span idx[order[k]]
+                if getattr(s, "surface_first", False):      # rank r meshed its spans in this order: table entry k belongs to span idx[order[k]]
                     idx = idx[self._tables[2 * nt + s.base_t[r]: 2 * nt + s.base_t[r] + len(idx)]]
                 ov = tv_h[s.base_t[r]: s.base_t[r + 1]]
                 oi = ti_h[s.base_t[r]: s.base_t[r + 1]]

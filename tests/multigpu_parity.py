@@ -49,7 +49,10 @@ direct = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), 
                              direct=True)
 packed = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
                              wire_quads=True)
-ordered = PeerGatherScheduler(dist, torch, ctx, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
+# (a context reports its packed-wire progress to ONE scheduler's words: the second packed scheduler gets its own context)
+ctx_o = cb.Context(local)
+ctx_o.set_stream(torch.cuda.current_stream().cuda_stream)
+ordered = PeerGatherScheduler(dist, torch, ctx_o, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
                               wire_quads=True, surface_first=True)
 host = HostGatherScheduler(dist, ctx, rank, world, len(spans), [cap_v] * world, [cap_i] * world)
 for _ in range(2):

@@ -102,3 +102,30 @@ def test_round_robin_sharding_covers_every_span_once():
             assert np.array_equal(allidx, np.arange(n))
             sizes = [len(p) for p in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_lazy_gather_maps_surface_first_tables_back_to_the_callers_span_order():
+    """LazyGather._build without a GPU: two ranks, the second meshed its three spans in the order (2, 0, 1); the
+    per-span ranges rank 0 assembles must be in the caller's span order either way."""
+    from types import SimpleNamespace
+    from cantucci_b200.scheduler import LazyGather, shard_indices
+    shards = [shard_indices(6, 2, r, "block") for r in range(2)]
+    base_t = np.array([0, 4, 8]); base_v = np.array([0, 100, 200]); base_i = np.array([0, 600, 1200])
+    counts = np.array([5, 0, 7, 1, 2, 3])                       # vertices per span, caller order
+    order1 = np.array([2, 0, 1])                                # rank 1: table entry k = its local span order1[k]
+    tv = np.concatenate([np.concatenate([[0], np.cumsum(counts[shards[0]])]),
+                         np.concatenate([[0], np.cumsum(counts[shards[1]][order1])])])
+    ti = 6 * tv
+    orders = np.concatenate([np.arange(3), [0], order1, [0]])
+    for surface_first, tables in ((True, np.concatenate([tv, ti, orders])), (False, np.concatenate([tv, ti]))):
+        s = SimpleNamespace(nspans=6, world=2, shards=shards, base_t=base_t, base_v=base_v, base_i=base_i,
+                            surface_first=surface_first, _views=(None, None, None))
+        g = LazyGather(s, tables.astype(np.int64))
+        got = (g.span_v[:, 1] - g.span_v[:, 0])
+        if surface_first:
+            assert np.array_equal(got, counts)
+            assert np.array_equal(g.span_i[:, 1] - g.span_i[:, 0], 6 * counts)
+            assert g.span_v[5, 0] == 100 + 0 and g.span_v[3, 0] == 100 + 3      # rank 1's region starts with span 5
+        else:       # the same tables read without the order section: entries stay in table order
+            assert np.array_equal(got[:3], counts[:3]) and np.array_equal(got[3:], counts[3:][order1])
+        assert g.n_vertices == counts.sum() and g.n_indices == 6 * counts.sum()
