@@ -398,10 +398,11 @@ def ours_main(args):
     # ======================================================================== headline: weak scaling ====
     volume = workload_spans(args.tiles)
     spans = volume if world == 1 else np.ascontiguousarray(np.tile(volume, (world, 1)))
-    # (N > 4, where rank 0's ingest bounds the gather: the sending ranks mesh their spans surface-first -- the order is
-    # computed inside every step, ctc_order_spans -- so that the bytes travel early and the last launch groups leave no tail)
+    # (--surface-first: the sending ranks mesh their spans in ctc_order_spans' order, computed inside every step.  Measured
+    # and NOT the default: at 8 GPUs rank 0's ingest is saturated for the whole step, not only in its tail, and seven
+    # senders bursting early make it worse -- 7.86 against 7.25 ms, profiles/bench_n8_order_ab_r2.json)
     sched, local_spans, info = make_scheduler(spans, "block", args.gather, wire_packed_from=5,
-                                              surface_first=(world > 4 or args.surface_first) and not args.caller_order)
+                                              surface_first=args.surface_first and not args.caller_order)
     nspans, total_samples = info["nspans"], info["nspans"] * n3
     step = lambda: run_step(sched, spans, local_spans)
 
@@ -429,6 +430,26 @@ def ours_main(args):
     kernel_ms = ctx.kernel_times()
     ctx.set_overlap(True); ctx.set_kernel_timing(False)
     value = total_samples / (ms_per_step * 1e-3)
+
+    # ---- --ab-order (N > 1): the same weak step with the OTHER span order, back to back in this process ----------
+    order_ab = None
+    if args.ab_order and world > 1 and args.gather == "peer":
+        ctx_b = cb.Context(local_rank)               # (its own context: packed-wire progress words are per context)
+        ctx_b.set_stream(stream.cuda_stream)
+        ctx_a, ctx = ctx, ctx_b
+        try:
+            sched_b, local_b, info_b = make_scheduler(spans, "block", args.gather, wire_packed_from=5 if not args.wire_packed else 0,
+                                                      surface_first=not info["surface_first"])
+            step_b = lambda: run_step(sched_b, spans, local_b)
+            for _ in range(args.warmup):
+                step_b()
+            ms_b = timed_steps(step_b, args.steps)
+            sched_b.close()
+        finally:
+            ctx = ctx_a
+        ms_a = timed_steps(step, args.steps)         # ... and the headline order once more, after it
+        order_ab = {"surface_first_ms": ms_a if info["surface_first"] else ms_b, "caller_order_ms": ms_b if info["surface_first"] else ms_a,
+                    "headline_ms": ms_per_step, "steps": args.steps}
 
     # ======================================================================== BASELINE config 5: strong scaling ====
     strong = None
@@ -472,7 +493,7 @@ def ours_main(args):
     # shared, page-locked host segment, i.e. the device->host copies of the N ranks run in parallel over N PCIe
     # links; rank 0 reads all offset tables there.
     e2e_multi = None
-    if world > 1:
+    if world > 1 and not args.no_e2e:
         import shutil
         need = int((info["nv_tot"] * 28 + info["ni_tot"] * 4) * 1.1) + (64 << 20)
         flag = torch.tensor([1 if (rank != 0 or shutil.disk_usage("/dev/shm").free > need) else 0], dtype=torch.int64, device=device)
@@ -670,7 +691,8 @@ def ours_main(args):
                                            "NVLink, pipelined behind compute)" if args.gather == "peer" else " by grouped NCCL send/recv"))),
                         "index_wire": "packed 8-byte quads, widened on rank 0" if info["packed"] else "six u32 per quad",
                         "span_order": ("senders mesh surface-first (ctc_order_spans inside every step; rank 0 maps the tables back to the "
-                                       "caller's span order)") if info["surface_first"] else "caller order"},
+                                       "caller's span order)") if info["surface_first"] else "caller order",
+                        "span_order_ab": order_ab},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
             "vertices": info["nv_tot"], "indices": info["ni_tot"], "gathered_bytes_per_step": info["gathered_bytes"],
             "gpu_launches": int(launches2 - launches1),
@@ -816,7 +838,9 @@ def main():
     ap.add_argument("--group-spans", type=int, default=0, help="spans per launch group (0 = library default)")
     ap.add_argument("--wire-packed", action="store_true", help="N>1: force packed quad records (default only for N > 4)")
     ap.add_argument("--caller-order", action="store_true", help="never re-order spans (e2e leg, senders of the N > 4 gather)")
-    ap.add_argument("--surface-first", action="store_true", help="N>1: senders mesh surface-first at every N (default only for N > 4)")
+    ap.add_argument("--surface-first", action="store_true", help="N>1: senders mesh surface-first (measured slower at 8 GPUs; off by default)")
+    ap.add_argument("--ab-order", action="store_true", help="N>1: also time the weak step with the other span order")
+    ap.add_argument("--no-e2e", action="store_true", help="N>1: skip the host-gather e2e leg")
     ap.add_argument("--wire-u32", action="store_true",
                     help="N>1, --gather peer: ship six u32 indices per quad instead of packed 8-byte quad records")
     ap.add_argument("--gather", default="peer", choices=["peer", "direct", "nccl"],

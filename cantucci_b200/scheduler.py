@@ -233,8 +233,10 @@ class PeerGatherScheduler:
         """surface_first = True: every SENDING rank meshes its spans in ctc_order_spans' order (the spans most likely
         to hold surface first, provably empty ones last), so its puts start with the first launch group and the
         groups computed last leave nothing in flight when the kernels end -- rank 0's ingest is the bound of the
-        gather at 8 GPUs, and what it cannot hide is the tail.  The order is computed inside every step and travels
-        with the offset tables; the per-span ranges rank 0 assembles are in the caller's span order as before.
+        gather at 8 GPUs.  The order is computed inside every step and travels with the offset tables; the per-span
+        ranges rank 0 assembles are in the caller's span order as before.  MEASURED AND NOT USED BY bench.py: at 8 GPUs
+        rank 0's ingest is saturated through the whole step, not only in its tail, and seven senders bursting early make
+        it worse (7.86 against 7.25 ms, profiles/bench_n8_order_ab_r2.json); byte parity: tests/multigpu_parity.py.
         (A context reports its packed-wire progress to the words of ONE scheduler: give every wire_quads scheduler of
         a process its own Context.)
         wire_quads = True (copy-engine mode only): ranks > 0 ship one packed 8-byte record per quad
