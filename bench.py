@@ -633,7 +633,7 @@ def ours_main(args):
             packed_wire = wire1[0] - wire0[0] == args.steps and wire1[1] == wire0[1]
             nv, ni = int(v_off[nspans]), int(i_off[nspans])
             e2e = {"value": total_samples / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(nspans * 48),
-                   "d2h_bytes_per_step": int(nv * 28 + (ni // 6 * 8 if packed_wire else ni * 4) + 2 * (nspans + 1) * 8 + 48),
+                   "d2h_bytes_per_step": int(ctx.mesh_d2h_bytes() + 2 * (nspans + 1) * 8 + 48),
                    "api": ("ctc_order_spans + ctc_mesh_spans" if e2e_ordered else "ctc_mesh_spans") + " (host pointers; pinned host buffers)",
                    "span_order": ("surface-first: planned inside every step by ctc_order_spans (one DE evaluation per span), the copy "
                                   "pipeline starts with the first launch group") if e2e_ordered else "caller order",

@@ -73,7 +73,7 @@ EXPORTS = (
     "ctc_ctx_set_coalescing", "ctc_ctx_coalescing_stats", "ctc_ctx_set_host_index_wire", "ctc_ctx_host_index_wire_stats", "ctc_ctx_set_wire_progress", "ctc_cull_spans", "ctc_expand_quads_host", "ctc_render", "ctc_render_device",
     "ctc_last_error_copy", "ctc_multi_create", "ctc_multi_destroy", "ctc_multi_ngpus", "ctc_multi_ctx",
     "ctc_multi_last_error", "ctc_mesh_spans_multi", "ctc_mesh_spans_multi_device", "ctc_multi_shard_plan",
-    "ctc_interop_alloc", "ctc_interop_import", "ctc_interop_free", "ctc_device_read", "ctc_device_write", "ctc_order_spans",
+    "ctc_interop_alloc", "ctc_interop_import", "ctc_interop_free", "ctc_device_read", "ctc_device_write", "ctc_order_spans", "ctc_ctx_set_host_wire_share", "ctc_mesh_d2h_bytes",
 )
 
 _lib = None
@@ -154,6 +154,10 @@ def lib() -> C.CDLL:
     L.ctc_interop_free.argtypes = [vp, vp]
     L.ctc_order_spans.restype = C.c_int
     L.ctc_order_spans.argtypes = [vp, shp, spn, sz, u32, vp]
+    L.ctc_ctx_set_host_wire_share.restype = C.c_int
+    L.ctc_ctx_set_host_wire_share.argtypes = [vp, u32, u32]
+    L.ctc_mesh_d2h_bytes.restype = C.c_int
+    L.ctc_mesh_d2h_bytes.argtypes = [vp, u64p]
     L.ctc_device_write.restype = C.c_int
     L.ctc_device_write.argtypes = [vp, vp, vp, sz]
     L.ctc_device_read.restype = C.c_int
@@ -257,6 +261,15 @@ class Context:
         """Host destinations of ctc_mesh_spans: packed quad records over PCIe, widened by host threads.
         0 / False: off; 1 / True (default): calls of >= 128 spans; 2: every call."""
         self.check(lib().ctc_ctx_set_host_index_wire(self._h, int(mode)))
+
+    def set_host_wire_share(self, num: int, den: int):
+        """Of every `den` launch groups of a large host-buffer call, `num` ship their indices as packed records."""
+        self.check(lib().ctc_ctx_set_host_wire_share(self._h, num, den))
+
+    def mesh_d2h_bytes(self) -> int:
+        b = C.c_uint64(0)
+        self.check(lib().ctc_mesh_d2h_bytes(self._h, C.byref(b)))
+        return int(b.value)
 
     def host_index_wire_stats(self):
         """(calls that used the packed wire, calls that fell back to u32 indices, widening threads)."""

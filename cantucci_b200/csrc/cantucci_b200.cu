@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -140,7 +141,9 @@ public:
     bool start(int device, int share = 1) {      // share: contexts of this process that run such a pool side by side
         if (!th_.empty()) return true;
         const unsigned hw = std::thread::hardware_concurrency();
-        int n = hw >= 8 ? (int)hw / 2 : (hw >= 2 ? (int)hw - 1 : 1);
+        // (the widening is bound by the host's memory system, not by cores -- 4 / 8 / 16 threads on a 16-thread host: 13.8 /
+        // 12.5 / 12.2 ms per benched volume -- and the caller's own pool waits in this call: all but two hardware threads)
+        int n = hw >= 8 ? (int)hw - 2 : (hw >= 2 ? (int)hw - 1 : 1);
         if (share > 1) { n /= share; if (n < 2) n = 2; }
         if (const char* e = getenv("CANTUCCI_B200_EXPAND_THREADS")) { const int v = atoi(e); if (v >= 1) n = v; }
         if (n > 32) n = 32;
@@ -246,6 +249,13 @@ struct ctc_ctx {
     // host destinations: indices cross PCIe as packed quad records and are widened by host threads (default on;
     // a span with >= 65536 vertices makes the call fall back to u32 indices on the wire)
     int host_wire = 1;          // ctc_ctx_set_host_index_wire: 0 off, 1 calls of >= 128 spans, 2 every call
+    // ... of every hybrid_den launch groups hybrid_num go packed (widened by host threads), the others as six u32 per quad
+    // straight into the caller's buffer: the packed wire loads the host's memory system, the u32 wire the PCIe link.
+    // Measured on the benched volume (scripts/gpu_e2e_share.py): 4/4 10.5-10.8 ms, 3/4 11.2, 2/4 11.8, 1/4 13.7, 0/4 13.0
+    // -- the link is the scarcer resource on the measured hosts, so everything travels packed by default.
+    int hybrid_num = 1, hybrid_den = 1;        // CANTUCCI_B200_HOST_WIRE_SHARE = "num/den"
+    std::vector<uint8_t> group_packed;         // per launch group of the last pipelined call
+    uint64_t last_d2h_bytes = 0;               // mesh bytes the last host-pointer call copied device -> host
     bool last_wire_overflow = false;
     uint64_t host_wire_calls = 0, host_wire_fallbacks = 0;
     HostExpander expander;
@@ -263,7 +273,7 @@ struct ctc_ctx {
     // workspace
     DevBuf suspects, suspect_count;               // fast mode: K1's suspect lists (double-buffered like the grids)
     DevBuf geom, grids, sign_bits, m_active, word_vpre, cell_of, quad_of, span_first, neg8, chunk_cnt, span_tot, span_pre, state;
-    DevBuf out_v, out_idx, off_v, off_i;          // host-pointer entry points
+    DevBuf out_v, out_idx, out_wire, off_v, off_i; // host-pointer entry points (out_wire: packed quad records of the hybrid index wire)
     DevBuf pts_in, pts_out;
     PinnedBuf h_geom, h_state, h_tables, h_pts;
 
@@ -597,7 +607,9 @@ int ensure_progress(ctc_ctx* ctx, size_t groups) {
 
 int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans, size_t nspans, uint32_t R,
                     ctc_vertex* d_v, size_t vcap, uint32_t* d_idx, size_t icap, uint64_t* d_v_off, uint64_t* d_i_off,
-                    bool pipeline = false, bool packed_quads = false) {
+                    bool pipeline = false, int packed_quads = 0 /* 1: every group, 2: hybrid_num of hybrid_den groups */,
+                    const std::function<int(size_t)>* on_group = nullptr /* called with the number of groups enqueued so far */,
+                    uint2* d_wire = nullptr /* packed records go here (at quad offsets) instead of into d_idx */) {
     ShapeDev sh; uint32_t lg;
     int rc = check_shape(ctx, shape, &sh); if (rc) return rc;
     rc = check_spans(ctx, spans, nspans, R, &lg); if (rc) return rc;
@@ -701,6 +713,7 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         CK(cudaStreamWaitEvent(sE, ctx->k1_done[0], 0));
     }
     if (pipeline) {
+        ctx->group_packed.assign(n_groups, 0);
         rc = ensure_progress(ctx, n_groups); if (rc) return rc;
         while (ctx->group_events.size() < n_groups) {
             cudaEvent_t e;
@@ -768,14 +781,20 @@ int mesh_spans_impl(ctc_ctx* ctx, const ctc_shape* shape, const ctc_span* spans,
         }
         {   // pass 3
             PassTimer t(ctx, 2, sE);
-            if (pipeline && packed_quads)
-                quad_kernel<true><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st, d_idx, (unsigned long long)icap);
+            const bool pk = pipeline && (packed_quads == 1 ||
+                                         (packed_quads == 2 && (gi * (size_t)ctx->hybrid_num) / ctx->hybrid_den != ((gi + 1) * (size_t)ctx->hybrid_num) / ctx->hybrid_den));
+            if (pipeline) ctx->group_packed[gi] = pk ? 1 : 0;
+            if (pk)
+                quad_kernel<true><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st,
+                                                                d_wire ? reinterpret_cast<uint32_t*>(d_wire) : d_idx, (unsigned long long)icap);
             else
                 quad_kernel<false><<<vblocks, kThreads, 0, sE>>>(ls, R, lg, gp.words_per_span, st, d_idx, (unsigned long long)icap);
             ctx->launches++;
         }
         if (pipeline) CK(cudaEventRecord(ctx->group_events[gi], sE));
         if (two_streams) CK(cudaEventRecord(ctx->ext_done[gi], sE));
+        // (the host-pointer call starts copying the groups that have already finished while the rest is being enqueued)
+        if (pipeline && on_group && gi + 1 < n_groups) { rc = (*on_group)(gi + 1); if (rc) return rc; }
     }
     // the caller's stream owns completion: it joins the extraction stream
     if (two_streams) CK(cudaStreamWaitEvent(sA, ctx->ext_done[n_groups - 1], 0));
@@ -855,6 +874,10 @@ int ctc_ctx_create(int device, ctc_ctx** out) {
         (void)cudaGetLastError(); delete c; return CTC_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    if (const char* e = getenv("CANTUCCI_B200_HOST_WIRE_SHARE")) {        // "num/den" (measurement runs)
+        int num = 0, den = 0;
+        if (sscanf(e, "%d/%d", &num, &den) == 2 && den > 0 && den <= 1024 && num >= 0 && num <= den) { c->hybrid_num = num; c->hybrid_den = den; }
+    }
     *out = c;
     return CTC_OK;
 }
@@ -864,7 +887,7 @@ void ctc_ctx_destroy(ctc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->geom, &c->grids, &c->m_active, &c->sign_bits, &c->word_vpre, &c->cell_of, &c->quad_of,
-                      &c->span_first, &c->neg8, &c->chunk_cnt, &c->span_tot, &c->span_pre, &c->state, &c->out_v, &c->out_idx,
+                      &c->span_first, &c->neg8, &c->chunk_cnt, &c->span_tot, &c->span_pre, &c->state, &c->out_v, &c->out_idx, &c->out_wire,
                       &c->off_v, &c->off_i, &c->pts_in, &c->pts_out, &c->suspects, &c->suspect_count})
         b->release();
     interop_release_all(c);
@@ -940,6 +963,20 @@ int ctc_ctx_set_host_index_wire(ctc_ctx* ctx, int packed_quads) {
     if (!ctx) return CTC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->host_wire = packed_quads < 0 ? 0 : (packed_quads > 2 ? 2 : packed_quads);
+    return CTC_OK;
+}
+
+int ctc_ctx_set_host_wire_share(ctc_ctx* ctx, uint32_t num, uint32_t den) {
+    if (!ctx || den == 0 || den > 1024 || num > den) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->hybrid_num = (int)num; ctx->hybrid_den = (int)den;
+    return CTC_OK;
+}
+
+int ctc_mesh_d2h_bytes(ctc_ctx* ctx, uint64_t* bytes) {
+    if (!ctx || !bytes) return CTC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *bytes = ctx->last_d2h_bytes;
     return CTC_OK;
 }
 
@@ -1094,21 +1131,106 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
     bool stage_v = nspans > 8 && v && vcap && pageable(v);
     bool stage_i = nspans > 8 && !host_wire && !ctx->wire_quads && idx && icap && pageable(idx);
     if ((host_wire || stage_v || stage_i) && !ctx->expander.start(ctx->device, ctx->expander_share)) host_wire = stage_v = stage_i = false;
-    if (host_wire) CK(ctx->h_wire.ensure((icap / 6 + 1) * sizeof(uint2)));
+    if (host_wire) { CK(ctx->h_wire.ensure((icap / 6 + 1) * sizeof(uint2))); CK(ctx->out_wire.ensure((icap / 6 + 1) * sizeof(uint2))); }
     if (stage_i && ctx->h_wire.ensure(icap * sizeof(uint32_t)) != cudaSuccess) { (void)cudaGetLastError(); stage_i = false; }
     if (stage_v && ctx->h_vstage.ensure(vcap * sizeof(ctc_vertex)) != cudaSuccess) { (void)cudaGetLastError(); stage_v = false; }
-    const bool packed = ctx->wire_quads || host_wire;
+    // (hybrid only towards page-locked index buffers: a u32 group copied straight into PAGEABLE memory would be a staged copy)
+    const int packed = ctx->wire_quads ? 1 : (host_wire ? ((ctx->hybrid_num >= ctx->hybrid_den || pageable(idx)) ? 1 : 2) : 0);
+    ctx->last_d2h_bytes = 0;
     const bool workers = host_wire || stage_v || stage_i;
+    if (workers) {
+        ctx->expander.begin();
+        if (host_wire) ctx->host_wire_calls++;
+    }
+    unsigned long long* wprog = nullptr;
+    unsigned long long wtag = 0;
+    const bool want_prog = ctx->wire_progress && ctx->wire_quads && !workers;
+    if (want_prog) {     // (one word per launch group + the closing one; sized up front: the words are sources of async copies)
+        wtag = (++ctx->wire_epoch & 0x7FFFFFull) << 40;
+        CK(ctx->h_wire_prog.ensure((nspans + 2) * 8));
+        wprog = static_cast<unsigned long long*>(ctx->h_wire_prog.p);
+    }
+    // Each launch group's slice of the mesh is copied on a second stream as soon as that group has finished, while
+    // the following groups are still computing -- or still being ENQUEUED: `issue` is also called (non-blocking) from
+    // the enqueue loop, so the first, small groups are on their way before the last launch has been made.
+    size_t done_v = 0, done_i = 0, next_g = 0;
+    int copy_rc = CTC_OK;
+    auto issue = [&](size_t upto, bool blocking) -> int {
+        if (workers)
+            while (ctx->wire_events.size() < 2 * upto) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->wire_events.push_back(e);
+            }
+        for (; next_g < upto && copy_rc == CTC_OK; ++next_g) {
+            const size_t g = next_g;
+            cudaError_t e;
+            if (blocking) e = cudaEventSynchronize(ctx->group_events[g]);
+            else { e = cudaEventQuery(ctx->group_events[g]); if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return CTC_OK; } }
+            if (trace && g == 0) t_first = since();
+            const unsigned long long tv = ctx->progress_h[2 * g], ti = 6ull * ctx->progress_h[2 * g + 1];
+            const size_t cv = tv < vcap ? (size_t)tv : vcap, ci = ti < icap ? (size_t)ti : icap;
+            if (e == cudaSuccess && cv > done_v) {
+                ctx->last_d2h_bytes += (cv - done_v) * sizeof(ctc_vertex);
+                if (stage_v) {
+                    ctc_vertex* hv = static_cast<ctc_vertex*>(ctx->h_vstage.p);
+                    const size_t bytes = (cv - done_v) * sizeof(ctc_vertex);
+                    e = cudaMemcpyAsync(hv + done_v, ctx->out_v.as<ctc_vertex>() + done_v, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+                    cudaEvent_t ev = ctx->wire_events[2 * g + 1];
+                    if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->copy_stream);
+                    if (e == cudaSuccess) ctx->expander.push(ExpandTask{ev, hv + done_v, v + done_v, (bytes + 15) / 16, 1, bytes});
+                } else {
+                    e = cudaMemcpyAsync(v + done_v, ctx->out_v.as<ctc_vertex>() + done_v, (cv - done_v) * sizeof(ctc_vertex),
+                                        cudaMemcpyDefault, ctx->copy_stream);
+                }
+                done_v = cv;
+            }
+            if (e == cudaSuccess && ci > done_i) {
+                const size_t q0 = done_i / 6, q1 = ci / 6;
+                if (host_wire && ctx->group_packed[g]) {   // packed records to the pinned wire buffer; host threads widen them into idx
+                    uint2* hw = static_cast<uint2*>(ctx->h_wire.p);
+                    ctx->last_d2h_bytes += (q1 - q0) * sizeof(uint2);
+                    e = cudaMemcpyAsync(hw + q0, ctx->out_wire.as<uint2>() + q0, (q1 - q0) * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->copy_stream2);
+                    if (e == cudaSuccess) e = cudaEventRecord(ctx->wire_events[2 * g], ctx->copy_stream2);
+                    if (e == cudaSuccess) ctx->expander.push(ExpandTask{ctx->wire_events[2 * g], hw + q0, idx + 6 * q0, q1 - q0, 0, 0});
+                } else if (stage_i) {
+                    uint32_t* hi = static_cast<uint32_t*>(ctx->h_wire.p);
+                    const size_t bytes = (ci - done_i) * sizeof(uint32_t);
+                    ctx->last_d2h_bytes += bytes;
+                    e = cudaMemcpyAsync(hi + done_i, ctx->out_idx.as<uint32_t>() + done_i, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream2);
+                    if (e == cudaSuccess) e = cudaEventRecord(ctx->wire_events[2 * g], ctx->copy_stream2);
+                    if (e == cudaSuccess) ctx->expander.push(ExpandTask{ctx->wire_events[2 * g], hi + done_i, idx + done_i, (bytes + 15) / 16, 1, bytes});
+                } else if (ctx->wire_quads) {      // packed records: 8 bytes per quad (= per 6 indices), densely at quad offsets
+                    e = cudaMemcpyAsync(reinterpret_cast<uint2*>(idx) + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2),
+                                        cudaMemcpyDefault, ctx->copy_stream2);
+                    if (wprog && e == cudaSuccess) {       // ... and the word that says how far the records have come
+                        wprog[g] = wtag | (unsigned long long)q1;
+                        e = cudaMemcpyAsync(ctx->wire_progress, wprog + g, 8, cudaMemcpyDefault, ctx->copy_stream2);
+                    }
+                } else {
+                    ctx->last_d2h_bytes += (ci - done_i) * sizeof(uint32_t);
+                    e = cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
+                                        cudaMemcpyDefault, ctx->copy_stream2);
+                }
+                done_i = ci;
+            }
+            if (e != cudaSuccess) copy_rc = fail_cuda(ctx, e, "pipelined device->host copy");
+        }
+        return CTC_OK;
+    };
+    const std::function<int(size_t)> during_enqueue = [&](size_t enqueued) { return issue(enqueued, false); };
     int rc = mesh_spans_impl(ctx, shape, spans, nspans, resolution, ctx->out_v.as<ctc_vertex>(), vcap,
                              ctx->out_idx.as<uint32_t>(), icap, ctx->off_v.as<uint64_t>(), ctx->off_i.as<uint64_t>(),
-                             /*pipeline=*/true, packed);
-    if (rc) return rc;
+                             /*pipeline=*/true, packed, &during_enqueue, host_wire ? ctx->out_wire.as<uint2>() : nullptr);
+    if (rc) {
+        if (workers) ctx->expander.finish();
+        cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->copy_stream2);
+        return rc;
+    }
     if (trace) t_enq = since();
     // Everything is enqueued.  The offset tables follow the kernels on the compute stream (straight
     // to the destination when it is device/peer memory, through a pinned staging buffer when it is
-    // host memory, so the call never blocks on a pageable copy); each group's slice of the mesh is
-    // copied on a second stream as soon as that group has finished, while the following groups are
-    // still computing.
+    // host memory, so the call never blocks on a pageable copy).
     cudaPointerAttributes pa{};
     const bool tables_on_device = cudaPointerGetAttributes(&pa, v_off) == cudaSuccess &&
                                   (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
@@ -1124,70 +1246,9 @@ static int mesh_spans_host_once(ctc_ctx* ctx, const ctc_shape* shape, const ctc_
     }
     CK(ctx->h_state.ensure(sizeof(MeshState)));
     CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, sizeof(MeshState), cudaMemcpyDeviceToHost, ctx->stream));
-    if (workers) {
-        while (ctx->wire_events.size() < 2 * ctx->n_groups) {
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ctx->wire_events.push_back(e);
-        }
-        ctx->expander.begin();
-        if (host_wire) ctx->host_wire_calls++;
-    }
-    unsigned long long* wprog = nullptr;
-    unsigned long long wtag = 0;
-    if (ctx->wire_progress && ctx->wire_quads && !workers) {
-        CK(ctx->h_wire_prog.ensure((ctx->n_groups + 2) * 8));
-        wprog = static_cast<unsigned long long*>(ctx->h_wire_prog.p);
-        wtag = (++ctx->wire_epoch & 0x7FFFFFull) << 40;
-    }
-    size_t done_v = 0, done_i = 0;
-    int copy_rc = CTC_OK;
-    for (size_t g = 0; g < ctx->n_groups && copy_rc == CTC_OK; ++g) {
-        cudaError_t e = cudaEventSynchronize(ctx->group_events[g]);
-        if (trace && g == 0) t_first = since();
-        const unsigned long long tv = ctx->progress_h[2 * g], ti = 6ull * ctx->progress_h[2 * g + 1];
-        const size_t cv = tv < vcap ? (size_t)tv : vcap, ci = ti < icap ? (size_t)ti : icap;
-        if (e == cudaSuccess && cv > done_v) {
-            if (stage_v) {
-                ctc_vertex* hv = static_cast<ctc_vertex*>(ctx->h_vstage.p);
-                const size_t bytes = (cv - done_v) * sizeof(ctc_vertex);
-                e = cudaMemcpyAsync(hv + done_v, ctx->out_v.as<ctc_vertex>() + done_v, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
-                cudaEvent_t ev = ctx->wire_events[ctx->n_groups + g];
-                if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->copy_stream);
-                if (e == cudaSuccess) ctx->expander.push(ExpandTask{ev, hv + done_v, v + done_v, (bytes + 15) / 16, 1, bytes});
-            } else {
-                e = cudaMemcpyAsync(v + done_v, ctx->out_v.as<ctc_vertex>() + done_v, (cv - done_v) * sizeof(ctc_vertex),
-                                    cudaMemcpyDefault, ctx->copy_stream);
-            }
-            done_v = cv;
-        }
-        if (e == cudaSuccess && ci > done_i) {
-            const size_t q0 = done_i / 6, q1 = ci / 6;
-            if (host_wire) {            // packed records to the pinned wire buffer; host threads widen them into idx
-                uint2* hw = static_cast<uint2*>(ctx->h_wire.p);
-                e = cudaMemcpyAsync(hw + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->copy_stream2);
-                if (e == cudaSuccess) e = cudaEventRecord(ctx->wire_events[g], ctx->copy_stream2);
-                if (e == cudaSuccess) ctx->expander.push(ExpandTask{ctx->wire_events[g], hw + q0, idx + 6 * q0, q1 - q0, 0, 0});
-            } else if (stage_i) {
-                uint32_t* hi = static_cast<uint32_t*>(ctx->h_wire.p);
-                const size_t bytes = (ci - done_i) * sizeof(uint32_t);
-                e = cudaMemcpyAsync(hi + done_i, ctx->out_idx.as<uint32_t>() + done_i, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream2);
-                if (e == cudaSuccess) e = cudaEventRecord(ctx->wire_events[g], ctx->copy_stream2);
-                if (e == cudaSuccess) ctx->expander.push(ExpandTask{ctx->wire_events[g], hi + done_i, idx + done_i, (bytes + 15) / 16, 1, bytes});
-            } else if (ctx->wire_quads) {      // packed records: 8 bytes per quad (= per 6 indices), densely at quad offsets
-                e = cudaMemcpyAsync(reinterpret_cast<uint2*>(idx) + q0, ctx->out_idx.as<uint2>() + q0, (q1 - q0) * sizeof(uint2),
-                                    cudaMemcpyDefault, ctx->copy_stream2);
-                if (wprog && e == cudaSuccess) {       // ... and the word that says how far the records have come
-                    wprog[g] = wtag | (unsigned long long)q1;
-                    e = cudaMemcpyAsync(ctx->wire_progress, wprog + g, 8, cudaMemcpyDefault, ctx->copy_stream2);
-                }
-            } else {
-                e = cudaMemcpyAsync(idx + done_i, ctx->out_idx.as<uint32_t>() + done_i, (ci - done_i) * sizeof(uint32_t),
-                                    cudaMemcpyDefault, ctx->copy_stream2);
-            }
-            done_i = ci;
-        }
-        if (e != cudaSuccess) copy_rc = fail_cuda(ctx, e, "pipelined device->host copy");
+    {
+        const int irc = issue(ctx->n_groups, true);        // the rest, blocking on each group's event
+        if (irc != CTC_OK && copy_rc == CTC_OK) copy_rc = irc;
     }
     if (wprog && copy_rc == CTC_OK) {        // the last word: everything of this call is there
         wprog[ctx->n_groups] = (1ull << 63) | wtag | (unsigned long long)(done_i / 6);

@@ -343,9 +343,17 @@ CTC_API int ctc_ctx_set_wire_progress(ctc_ctx *ctx, void *d_progress_word);
  * with >= 65536 vertices makes the call repeat itself with u32 indices on the wire (counted in `fallbacks`).
  * Calls of fewer than 128 spans are not PCIe-bound and keep six u32 per quad (2: packed records for every call).
  * 0: always copy six u32 per quad.  Independently of this switch, buffers in PAGEABLE host memory are filled
- * through pinned landing buffers by the same host threads (calls of more than 8 spans).  The pool has half the
+ * through pinned landing buffers by the same host threads (calls of more than 8 spans).  The pool has all but two
  * hardware threads (shared out over the devices of a ctc_multi); CANTUCCI_B200_EXPAND_THREADS overrides the count. */
 CTC_API int ctc_ctx_set_host_index_wire(ctc_ctx *ctx, int packed_quads);
+/* The packed wire loads the HOST's memory system (the widening threads read 8 and write 24 bytes per quad beside the
+ * DMA writes), the u32 wire loads the PCIe link.  Towards page-locked index buffers the call can mix them by
+ * launch group: of every `den` groups `num` travel packed, the others as six u32 per quad straight into the caller's
+ * buffer (num = den, the default: all packed -- the fastest split on the measured hosts, 10.5 / 11.2 / 11.8 / 13.7 /
+ * 13.0 ms per benched volume for 4/4, 3/4, 2/4, 1/4, 0/4; num = 0: none).  CANTUCCI_B200_HOST_WIRE_SHARE="num/den" sets the
+ * default of new contexts.  ctc_mesh_d2h_bytes: the mesh bytes the last host-pointer call copied device -> host. */
+CTC_API int ctc_ctx_set_host_wire_share(ctc_ctx *ctx, uint32_t num, uint32_t den);
+CTC_API int ctc_mesh_d2h_bytes(ctc_ctx *ctx, uint64_t *bytes);
 CTC_API int ctc_ctx_host_index_wire_stats(ctc_ctx *ctx, uint64_t *calls, uint64_t *fallbacks, uint32_t *threads);
 
 /* Page-lock / unlock host memory the caller owns (cudaHostRegister, portable), e.g. a POSIX shared-

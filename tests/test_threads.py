@@ -103,3 +103,42 @@ def test_concurrent_single_span_calls_are_coalesced(ctx):
     [t.join() for t in th]
     assert rcs[3] == _lib.CTC_ERR_OVERFLOW and int(tiny[2][1]) == int(ref[2][4] - ref[2][3])
     assert all(rc == 0 for k, rc in enumerate(rcs) if k != 3)
+
+
+@pytest.mark.gpu
+def test_hybrid_index_wire_delivers_the_same_buffers(ctx):
+    """ctc_ctx_set_host_wire_share: whichever launch groups ship packed quad records (widened by host threads) and
+    whichever ship six u32 per quad, a large host-buffer call into page-locked memory delivers identical buffers."""
+    import ctypes as C
+    import torch
+    import cantucci_b200 as cb
+    L = cb.lib()
+    shape = cb.Mandelbulb.classic(6, 2.5, fast=True)
+    sh = shape._ctc_shape()
+    spans = cb.tile_volume(shape.bounding_box(), 8)           # 512 spans at R = 32: ramped launch groups
+    ns = len(spans)
+    vcap, icap = 600_000, 3_600_000
+    v = torch.empty((vcap, 7), dtype=torch.float32).pin_memory()
+    i = torch.empty((icap,), dtype=torch.int32).pin_memory()
+    v_off = np.zeros(ns + 1, np.uint64); i_off = np.zeros(ns + 1, np.uint64)
+    ctx.set_group_spans(48)                                   # 11 launch groups
+    ctx.set_host_index_wire(2)                                # packed records for every call size
+    got = {}
+    try:
+        for num, den in ((1, 1), (1, 2), (1, 3), (0, 1)):
+            ctx.set_host_wire_share(num, den)
+            i.zero_()
+            ctx.check(L.ctc_mesh_spans(ctx.handle, C.byref(sh), spans.ctypes.data, ns, 32, v.data_ptr(), vcap, i.data_ptr(), icap,
+                                       v_off.ctypes.data, i_off.ctypes.data, None))
+            nv, ni = int(v_off[ns]), int(i_off[ns])
+            got[(num, den)] = (v.numpy()[:nv].copy(), i.numpy()[:ni].copy(), v_off.copy(), i_off.copy(), ctx.mesh_d2h_bytes())
+    finally:
+        ctx.set_host_wire_share(1, 1); ctx.set_group_spans(0); ctx.set_host_index_wire(1)
+    ref = got[(1, 1)]
+    assert ref[1].size > 0
+    for key, g in got.items():
+        assert np.array_equal(g[0].view(np.uint32), ref[0].view(np.uint32)) and np.array_equal(g[1], ref[1]), key
+        assert np.array_equal(g[2], ref[2]) and np.array_equal(g[3], ref[3]), key
+    nq = ref[1].size // 6
+    assert got[(1, 1)][4] == ref[0].shape[0] * 28 + nq * 8 and got[(0, 1)][4] == ref[0].shape[0] * 28 + nq * 24
+    assert got[(1, 1)][4] < got[(1, 2)][4] < got[(0, 1)][4]
