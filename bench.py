@@ -259,6 +259,14 @@ def gpu_volume_host(ctx, shape, spans: np.ndarray, vcap: int | None = None, icap
     return batch.vertices, batch.indices, batch.v_off, batch.i_off, planes
 
 
+def default_packed_senders(world: int):
+    """How many of the world - 1 senders ship packed quad records in the weak-scaling gather (None = all).  Packed
+    records cost rank 0 a widening pass that competes with its own kernels, u32 indices cost NVLink ingest.  Measured at
+    8 GPUs (profiles/bench_n8_packed_ab_r2.json): 0 / 2 / 3 / 4 / 5 / 7 packed senders = 8.40 / 7.72 / 7.26 / 7.03 / 7.04 /
+    7.25 ms per step -> four of seven."""
+    return max(1, round(4 * (world - 1) / 7)) if world > 4 else None
+
+
 def bench_config(world: int) -> dict:
     """The `config` both arms print (identical keys and values, so the driver can compare them)."""
     return {"workload": WORKLOAD, "volumes": world, "spans": world * TILES ** 3, "spans_per_volume": TILES ** 3,
@@ -344,7 +352,7 @@ def ours_main(args):
         max_span_v = int(probe.v_off[: len(local_spans) + 1].diff().max()) if len(local_spans) else 0
         return nv, ni, max_span_v
 
-    def make_scheduler(spans, shard_mode, gather, wire_packed_from, surface_first=False):
+    def make_scheduler(spans, shard_mode, gather, wire_packed_from, surface_first=False, packed_senders=None):
         """(scheduler, local spans, totals) for one job: `spans` sharded over the ranks, gathered to rank 0."""
         nspans = spans.shape[0]
         mine = shard_indices(nspans, world, rank, shard_mode)
@@ -359,20 +367,24 @@ def ours_main(args):
         # packed quad records pay off once rank 0's NVLink ingest is the bound (measured: 8 GPUs); they need every
         # span below 65536 vertices (checked on the sizing run)
         use_packed = gather == "peer" and not args.wire_u32 and int(mx[0]) < 65536 and (world >= wire_packed_from or args.wire_packed)
+        # ... for the LAST `packed_senders` ranks only (None: every sender): packed records cost rank 0 a widening pass that
+        # competes with its own kernels, u32 indices cost NVLink ingest -- a split balances the two
+        n_packed = (world - 1 if packed_senders is None else max(0, min(world - 1, packed_senders))) if use_packed else 0
+        use_packed = n_packed > 0
         if world > 1 and gather in ("peer", "direct"):
             caps = torch.zeros((world, 2), dtype=torch.int64, device=device)
             caps[rank, 0], caps[rank, 1] = pad(nv_loc), pad(ni_loc)
             dist.all_reduce(caps)
             caps = caps.cpu().numpy()
             sched = PeerGatherScheduler(dist, torch, ctx, rank, world, device, nspans, caps[:, 0].tolist(), caps[:, 1].tolist(),
-                                        mode=shard_mode, direct=(gather == "direct"), wire_quads=use_packed,
+                                        mode=shard_mode, direct=(gather == "direct"), wire_quads=set(range(world - n_packed, world)),
                                         surface_first=surface_first and gather == "peer")
         else:
             mesher = DeviceMesher(ctx, torch, device, pad(nv_loc), pad(ni_loc), len(mine))
             sched = SpanScheduler(dist, torch, rank, world, device, mesher, pad(nv_tot), pad(ni_tot), mode=shard_mode)
         info = {"nspans": nspans, "mine": len(mine), "nv_loc": nv_loc, "ni_loc": ni_loc, "nv_tot": nv_tot, "ni_tot": ni_tot,
-                "packed": bool(use_packed), "surface_first": bool(getattr(sched, "surface_first", False)),
-                "gathered_bytes": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) * (8 / 6 if use_packed else 4))}
+                "packed": bool(use_packed), "packed_senders": int(n_packed), "surface_first": bool(getattr(sched, "surface_first", False)),
+                "gathered_bytes": int((nv_tot - nv_loc) * 28 + (ni_tot - ni_loc) / max(world - 1, 1) * (n_packed * 8 / 6 + (world - 1 - n_packed) * 4))}
         return sched, local, info
 
     def run_step(sched, spans, local, allow_lerp_assert=False):
@@ -402,7 +414,8 @@ def ours_main(args):
     # and NOT the default: at 8 GPUs rank 0's ingest is saturated for the whole step, not only in its tail, and seven
     # senders bursting early make it worse -- 7.86 against 7.25 ms, profiles/bench_n8_order_ab_r2.json)
     sched, local_spans, info = make_scheduler(spans, "block", args.gather, wire_packed_from=5,
-                                              surface_first=args.surface_first and not args.caller_order)
+                                              surface_first=args.surface_first and not args.caller_order,
+                                              packed_senders=default_packed_senders(world) if args.packed_senders < 0 else args.packed_senders)
     nspans, total_samples = info["nspans"], info["nspans"] * n3
     step = lambda: run_step(sched, spans, local_spans)
 
@@ -430,6 +443,27 @@ def ours_main(args):
     kernel_ms = ctx.kernel_times()
     ctx.set_overlap(True); ctx.set_kernel_timing(False)
     value = total_samples / (ms_per_step * 1e-3)
+
+    # ---- --ab-packed K1,K2,... (N > 1): the same weak step with K of the senders on the packed wire, back to back ----
+    packed_ab = None
+    if args.ab_packed and world > 1 and args.gather == "peer":
+        packed_ab = {}
+        ctx_a = ctx
+        for k in [int(x) for x in args.ab_packed.split(",")]:
+            ctx = cb.Context(local_rank)             # (its own context: packed-wire progress words are per context)
+            ctx.set_stream(stream.cuda_stream)
+            try:
+                sched_b, local_b, info_b = make_scheduler(spans, "block", args.gather, wire_packed_from=0, packed_senders=k)
+                step_b = lambda: run_step(sched_b, spans, local_b)
+                for _ in range(args.warmup):
+                    step_b()
+                packed_ab[str(k)] = {"ms": timed_steps(step_b, args.steps), "gathered_bytes": info_b["gathered_bytes"]}
+                sched_b.close()
+                del sched_b
+                torch.cuda.empty_cache()
+            finally:
+                ctx = ctx_a
+        packed_ab["headline_again_ms"] = timed_steps(step, args.steps)
 
     # ---- --ab-order (N > 1): the same weak step with the OTHER span order, back to back in this process ----------
     order_ab = None
@@ -689,10 +723,11 @@ def ours_main(args):
                         "parallelism": (f"{world} volume(s) of {info['mine']} spans, one per rank (weak scaling), meshes gathered to rank 0"
                                         + ("" if world == 1 else (" by one-sided puts into rank 0's IPC-mapped buffers (copy engines over "
                                            "NVLink, pipelined behind compute)" if args.gather == "peer" else " by grouped NCCL send/recv"))),
-                        "index_wire": "packed 8-byte quads, widened on rank 0" if info["packed"] else "six u32 per quad",
+                        "index_wire": (f"packed 8-byte quads from {info['packed_senders']} of {world - 1} senders, widened on rank 0; six u32 per quad from the others"
+                                       if info["packed"] else "six u32 per quad"),
                         "span_order": ("senders mesh surface-first (ctc_order_spans inside every step; rank 0 maps the tables back to the "
                                        "caller's span order)") if info["surface_first"] else "caller order",
-                        "span_order_ab": order_ab},
+                        "span_order_ab": order_ab, "packed_senders": info["packed_senders"], "packed_senders_ab": packed_ab},
             "span_meshes_per_s": nspans / (ms_per_step * 1e-3),
             "vertices": info["nv_tot"], "indices": info["ni_tot"], "gathered_bytes_per_step": info["gathered_bytes"],
             "gpu_launches": int(launches2 - launches1),
@@ -839,6 +874,8 @@ def main():
     ap.add_argument("--wire-packed", action="store_true", help="N>1: force packed quad records (default only for N > 4)")
     ap.add_argument("--caller-order", action="store_true", help="never re-order spans (e2e leg, senders of the N > 4 gather)")
     ap.add_argument("--surface-first", action="store_true", help="N>1: senders mesh surface-first (measured slower at 8 GPUs; off by default)")
+    ap.add_argument("--packed-senders", type=int, default=-1, help="N>1: how many sender ranks use the packed quad wire (-1 = default)")
+    ap.add_argument("--ab-packed", default="", help="N>1: comma-separated sender counts to time the weak step with")
     ap.add_argument("--ab-order", action="store_true", help="N>1: also time the weak step with the other span order")
     ap.add_argument("--no-e2e", action="store_true", help="N>1: skip the host-gather e2e leg")
     ap.add_argument("--wire-u32", action="store_true",

@@ -229,7 +229,7 @@ class PeerGatherScheduler:
 
     def __init__(self, dist, torch, ctx: _lib.Context, rank: int, world: int, device, nspans: int,
                  caps_v: list, caps_i: list, mode: str = "interleave", direct: bool = False,
-                 wire_quads: bool = False, surface_first: bool = False):
+                 wire_quads=False, surface_first: bool = False):
         """surface_first = True: every SENDING rank meshes its spans in ctc_order_spans' order (the spans most likely
         to hold surface first, provably empty ones last), so its puts start with the first launch group and the
         groups computed last leave nothing in flight when the kernels end -- rank 0's ingest is the bound of the
@@ -239,6 +239,9 @@ class PeerGatherScheduler:
         it worse (7.86 against 7.25 ms, profiles/bench_n8_order_ab_r2.json); byte parity: tests/multigpu_parity.py.
         (A context reports its packed-wire progress to the words of ONE scheduler: give every wire_quads scheduler of
         a process its own Context.)
+        wire_quads may also be a collection of sender ranks: only THOSE ship packed records, the others six u32 per
+        quad straight into the gathered index buffer.  Packed records cost rank 0 a widening pass that competes with
+        its own kernels, u32 indices cost NVLink ingest: at 8 GPUs a split balances the two.
         wire_quads = True (copy-engine mode only): ranks > 0 ship one packed 8-byte record per quad
         instead of six u32 indices (a third of the index bytes, -31 % of the whole gather) into a wire
         buffer on rank 0, which widens them into the gathered index buffer after the barrier.
@@ -247,7 +250,15 @@ class PeerGatherScheduler:
         ranks > 0 store straight into rank 0's mapped region -- compute and gather are one kernel."""
         self.dist, self.torch, self.ctx, self.rank, self.world, self.device = dist, torch, ctx, rank, world, device
         self.nspans, self.mode, self.direct = nspans, mode, direct
-        self.wire_quads = bool(wire_quads) and not direct and world > 1
+        if isinstance(wire_quads, (bool, int, np.bool_)):
+            packed = set(range(1, world)) if wire_quads else set()
+        else:
+            packed = {int(r) for r in wire_quads if 0 < int(r) < world}
+        if direct or world <= 1:
+            packed = set()
+        self.packed_ranks = packed
+        self.wire_quads = bool(packed)                   # some sender ships packed records: wire buffer + progress words exist
+        self.wire_mine = rank in packed                  # ... this rank does
         self.surface_first = bool(surface_first) and world > 1
         self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
         self.n_r = [len(x) for x in self.shards]
@@ -291,7 +302,7 @@ class PeerGatherScheduler:
             if rank == 0:
                 self._ctx2 = _lib.Context(ctx.device)
                 self._poll_stream = torch.cuda.Stream(device=device)
-            else:
+            elif self.wire_mine:
                 ctx.check(L.ctc_ctx_set_wire_progress(ctx.handle, C.c_void_p(self.ptrs[4].value + 8 * rank)))
         # rank-local scratch for rank 0's own device call (offset tables live in the shared table buffers)
         self._views = None
@@ -305,7 +316,7 @@ class PeerGatherScheduler:
 
     def close(self):
         L = _lib.lib()
-        if self.wire_quads and self.rank != 0:
+        if self.wire_mine:
             L.ctc_ctx_set_wire_progress(self.ctx.handle, None)
         self._ctx2 = self._flags = None
         for p in self.ptrs:
@@ -344,14 +355,14 @@ class PeerGatherScheduler:
                 self._widen_arrivals()          # ... while this rank's own kernels run
             rc = L.ctc_mesh_result(ctx.handle, None, None, None)
         else:
-            if self.wire_quads:          # destination: this rank's slot of the wire buffer (8 bytes per quad)
+            if self.wire_mine:           # destination: this rank's slot of the wire buffer (8 bytes per quad)
                 pi = self.ptrs[3].value + int(self.base_i[rank]) // 6 * 8
                 L.ctc_ctx_set_index_wire(ctx.handle, 1)
             try:
                 rc = L.ctc_mesh_spans(ctx.handle, C.byref(shape_struct), local.ctypes.data, local.shape[0], resolution,
                                       pv, self.caps_v[rank], pi, self.caps_i[rank], tv, ti, None)
             finally:
-                if self.wire_quads:
+                if self.wire_mine:
                     L.ctc_ctx_set_index_wire(ctx.handle, 0)
         if rc == _lib.CTC_ERR_LERP_ASSERT and allow_lerp_assert:
             rc = _lib.CTC_OK
@@ -373,7 +384,7 @@ class PeerGatherScheduler:
         L, torch, world = _lib.lib(), self.torch, self.world
         c2 = self._ctx2
         done = [0] * world
-        open_ranks = set(range(1, world))
+        open_ranks = set(self.packed_ranks)
         tag = self._epoch & 0x7FFFFF
         t_end = time.perf_counter() + timeout_s
         while open_ranks:

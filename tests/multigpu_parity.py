@@ -54,6 +54,11 @@ ctx_o = cb.Context(local)
 ctx_o.set_stream(torch.cuda.current_stream().cuda_stream)
 ordered = PeerGatherScheduler(dist, torch, ctx_o, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
                               wire_quads=True, surface_first=True)
+# only the LAST sender ships packed records, the others six u32 per quad (the split bench.py uses at 8 GPUs)
+ctx_s = cb.Context(local)
+ctx_s.set_stream(torch.cuda.current_stream().cuda_stream)
+split = PeerGatherScheduler(dist, torch, ctx_s, rank, world, device, len(spans), [cap_v] * world, [cap_i] * world,
+                            wire_quads={world - 1})
 host = HostGatherScheduler(dist, ctx, rank, world, len(spans), [cap_v] * world, [cap_i] * world)
 for _ in range(2):
     g1 = nccl.run(sh, spans, R)
@@ -62,6 +67,7 @@ for _ in range(2):
     g4 = host.run(sh, spans, R)
     g5 = packed.run(sh, spans, R)
     g6 = ordered.run(sh, spans, R)
+    g7 = split.run(sh, spans, R)
     torch.cuda.synchronize()
 if rank == 0:
     check(g1, "nccl")
@@ -70,6 +76,7 @@ if rank == 0:
     check(g4, "host")
     check(g5, "packed quads")
     check(g6, "packed quads, senders mesh surface-first")
+    check(g7, "packed quads from the last sender only")
     print("MULTIGPU_PARITY_OK", world, g2.n_vertices, g2.n_indices, flush=True)
 dist.barrier()
 peer.close()
@@ -77,4 +84,5 @@ direct.close()
 host.close()
 packed.close()
 ordered.close()
+split.close()
 dist.destroy_process_group()
