@@ -31,6 +31,12 @@ def shard_indices(nspans: int, world: int, rank: int, mode: str = "interleave") 
     return np.arange(rank, nspans, world, dtype=np.int64)
 
 
+def host_threads_per_process(hardware_threads: int, processes: int) -> int:
+    """Widening threads of one process when `processes` one-GPU processes share a host: an equal share of all but
+    two hardware threads, at least two."""
+    return max(2, (max(hardware_threads, 1) - 2) // max(processes, 1))
+
+
 def plan_order(ctx, shape_struct, local: np.ndarray, resolution: int) -> np.ndarray:
     """ctc_order_spans over a rank's spans: int64 indices, surface-first."""
     order = np.zeros(local.shape[0], dtype=np.uint32)
@@ -467,6 +473,11 @@ class HostGatherScheduler:
         import mmap
         import os
         self.dist, self.ctx, self.rank, self.world, self.nspans, self.mode = dist, ctx, rank, world, nspans, mode
+        # The library's pool of widening threads takes all but two hardware threads of the host; here `world` one-GPU
+        # processes share that host, so every process gets its share (the pool starts with the first host-buffer call;
+        # an explicit CANTUCCI_B200_EXPAND_THREADS wins).
+        if world > 1:
+            os.environ.setdefault("CANTUCCI_B200_EXPAND_THREADS", str(host_threads_per_process(os.cpu_count() or 1, world)))
         self.shards = [shard_indices(nspans, world, r, mode) for r in range(world)]
         self.n_r = [len(x) for x in self.shards]
         self.caps_v = [(int(c) + 63) // 64 * 64 for c in caps_v]

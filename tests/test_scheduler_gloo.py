@@ -129,3 +129,9 @@ def test_lazy_gather_maps_surface_first_tables_back_to_the_callers_span_order():
         else:       # the same tables read without the order section: entries stay in table order
             assert np.array_equal(got[:3], counts[:3]) and np.array_equal(got[3:], counts[3:][order1])
         assert g.n_vertices == counts.sum() and g.n_indices == 6 * counts.sum()
+
+
+def test_host_threads_are_shared_out_over_the_processes_of_a_host():
+    from cantucci_b200.scheduler import host_threads_per_process
+    assert host_threads_per_process(32, 8) == 3 and host_threads_per_process(16, 2) == 7
+    assert host_threads_per_process(16, 1) == 14 and host_threads_per_process(4, 8) == 2 and host_threads_per_process(0, 0) == 2
