@@ -9,6 +9,7 @@
 //   octree::Span           src/octree/mod.rs:13-32
 //   mesh::Vertex           src/mesh/mod.rs:255-261
 //   MeshBuffer / Timings   src/mesh/buffer.rs:24-42, 398-405
+//   MeshView               src/mesh/view.rs:14-41   (the upload step, without the host round trip: MeshViews)
 // Same names, argument meaning and error behaviour: where the reference panics (assert!), these
 // throw cantucci::Panic.  The Rust binding itself is shown in INTEGRATION.md.
 #pragma once
@@ -159,6 +160,69 @@ struct MeshBuffer {
             out[k].vertices.assign(v.begin() + v_off[k], v.begin() + v_off[k + 1]);
             out[k].indices.assign(idx.begin() + i_off[k], idx.begin() + i_off[k + 1]);
         }
+        return {std::move(out), Timings{t.first_ms, t.second_ms, t.third_ms, uint32_t(t.vertices), uint32_t(t.faces)}};
+    }
+};
+
+// Cost-aware span order (ctc_order_spans; not in the reference, whose pool takes the jobs in tree order,
+// mesh/mod.rs:129-161): indices of `spans`, the ones most likely to hold surface first.
+inline std::vector<uint32_t> order_spans(const Context& ctx, const std::vector<Span>& spans, const Shape& shape, uint32_t resolution) {
+    std::vector<uint32_t> order(spans.size());
+    const ctc_shape d = shape.descriptor();
+    ctx.check(ctc_order_spans(ctx.get(), &d, reinterpret_cast<const ctc_span*>(spans.data()), spans.size(), resolution, order.data()));
+    return order;
+}
+
+// Device memory the renderer imports by file descriptor (ctc_interop_alloc): VkImportMemoryFdInfoKHR on the Vulkan
+// side, ctc_interop_import in another CUDA context or process.
+class InteropBuffer {
+public:
+    InteropBuffer(const Context& ctx, size_t bytes) : ctx_(&ctx) { ctx.check(ctc_interop_alloc(ctx.get(), bytes, &ptr_, &fd_, &bytes_)); }
+    ~InteropBuffer() { if (ptr_) ctc_interop_free(ctx_->get(), ptr_); }      // (the descriptor stays the caller's to close)
+    InteropBuffer(const InteropBuffer&) = delete;
+    InteropBuffer& operator=(const InteropBuffer&) = delete;
+    void* ptr() const { return ptr_; }
+    int fd() const { return fd_; }
+    size_t bytes() const { return bytes_; }        // the allocated size: VkMemoryAllocateInfo::allocationSize
+private:
+    const Context* ctx_; void* ptr_ = nullptr; int fd_ = -1; size_t bytes_ = 0;
+};
+
+// MeshView{vbuf, ibuf, num_indices} (view.rs:14-18) as byte ranges of the batch's two interop buffers: the vertex /
+// index buffer bindings of the span's draw call (view.rs:76-79; indices are span-local, base vertex 0).
+struct MeshView { uint64_t vertex_offset, index_offset; uint32_t num_vertices, num_indices; };
+
+struct MeshViews {
+    std::vector<uint64_t> v_off, i_off;            // per-span tables, in vertices / indices
+    MeshView view(size_t k) const {
+        return {v_off[k] * sizeof(Vertex), i_off[k] * 4, uint32_t(v_off[k + 1] - v_off[k]), uint32_t(i_off[k + 1] - i_off[k])};
+    }
+    size_t size() const { return v_off.empty() ? 0 : v_off.size() - 1; }
+
+    // generate_for_box + MeshView::new for every span without leaving the GPU (mesh/mod.rs:141-146): the meshes are
+    // written straight into `vbuf` / `ibuf`, only the two offset tables come back.  Throws std::length_error when a
+    // buffer is too small (what(): the required vertices and indices).
+    static std::pair<MeshViews, Timings> generate(const Context& ctx, const std::vector<Span>& spans, const Shape& shape,
+                                                  uint32_t resolution, const InteropBuffer& vbuf, const InteropBuffer& ibuf) {
+        const size_t n = spans.size();
+        const ctc_shape d = shape.descriptor();
+        void* tables = nullptr;
+        ctx.check(ctc_device_alloc(ctx.get(), 2 * (n + 1) * 8, &tables));
+        struct Free { const Context& c; void* p; ~Free() { ctc_device_free(c.get(), p); } } guard{ctx, tables};
+        uint64_t* d_v_off = static_cast<uint64_t*>(tables);
+        ctx.check(ctc_mesh_spans_device(ctx.get(), &d, reinterpret_cast<const ctc_span*>(spans.data()), n, resolution,
+                                        static_cast<ctc_vertex*>(vbuf.ptr()), vbuf.bytes() / sizeof(Vertex),
+                                        static_cast<uint32_t*>(ibuf.ptr()), ibuf.bytes() / 4, d_v_off, d_v_off + n + 1));
+        uint64_t nv = 0, ni = 0;
+        ctc_timings t{};
+        const int rc = ctc_mesh_result(ctx.get(), &nv, &ni, &t);
+        if (rc == CTC_ERR_OVERFLOW) throw std::length_error("interop buffers too small: need " + std::to_string(nv) + " vertices, " + std::to_string(ni) + " indices");
+        ctx.check(rc);
+        MeshViews out;
+        std::vector<uint64_t> both(2 * (n + 1));
+        ctx.check(ctc_device_read(ctx.get(), both.data(), tables, both.size() * 8));
+        out.v_off.assign(both.begin(), both.begin() + n + 1);
+        out.i_off.assign(both.begin() + n + 1, both.end());
         return {std::move(out), Timings{t.first_ms, t.second_ms, t.third_ms, uint32_t(t.vertices), uint32_t(t.faces)}};
     }
 };

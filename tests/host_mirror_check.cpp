@@ -35,5 +35,26 @@ int main(int argc, char** argv) {
     const float d = bulb.min_distance_from(ctx, {0.3f, 0.2f, 0.1f});
     uint32_t bits; std::memcpy(&bits, &d, 4);
     std::printf("de %08x\n", bits);
+    // N2: the same span (and an empty one) meshed straight into interop buffers; read back through the C ABI
+    {
+        const std::vector<Span> spans{Span{{0.9f, 0.9f, 0.9f}, {1.2f, 1.2f, 1.2f}}, Span{{0.f, 0.f, 0.f}, {0.6f, 0.6f, 0.6f}}};
+        InteropBuffer vbuf(ctx, 1 << 20), ibuf(ctx, 1 << 20);
+        auto [views, tv] = MeshViews::generate(ctx, spans, bulb, 16, vbuf, ibuf);
+        const MeshView w = views.view(1), e = views.view(0);
+        std::vector<Vertex> v(w.num_vertices); std::vector<uint32_t> i(w.num_indices);
+        ctx.check(ctc_device_read(ctx.get(), v.data(), static_cast<char*>(vbuf.ptr()) + w.vertex_offset, v.size() * sizeof(Vertex)));
+        ctx.check(ctc_device_read(ctx.get(), i.data(), static_cast<char*>(ibuf.ptr()) + w.index_offset, i.size() * 4));
+        const bool same = v.size() == mesh.vertices.size() && i == mesh.indices &&
+                          std::memcmp(v.data(), mesh.vertices.data(), v.size() * sizeof(Vertex)) == 0;
+        const std::vector<uint32_t> order = order_spans(ctx, spans, bulb, 16);
+        std::printf("interop fd %d empty %u same %d order %u %u\n", vbuf.fd() >= 0 ? 1 : 0, e.num_indices, same ? 1 : 0, order[0], order[1]);
+        // 64 copies of the surface span at R = 32 do not fit one allocation granule: the required sizes are reported
+        int small = 0;
+        InteropBuffer tiny(ctx, 28);
+        try { MeshViews::generate(ctx, std::vector<Span>(64, spans[1]), bulb, 32, tiny, ibuf); }
+        catch (const std::length_error&) { small = 1; }
+        catch (const std::exception&) { small = -1; }
+        std::printf("overflow %d\n", small);
+    }
     return 0;
 }

@@ -39,3 +39,6 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle):
     assert int(first[5], 16) == fnv(v.tobytes()) and int(first[7], 16) == fnv(i.tobytes())
     d = np.float32(oracle.min_distance_from(sh, (0.3, 0.2, 0.1)))
     assert out.splitlines()[1].split()[1] == f"{d.view(np.uint32):08x}"
+    # N2 mirror: the span meshed into interop buffers equals the host-buffer mesh; the empty span has an empty view;
+    # order_spans puts the surface span (index 1) before the empty corner span (index 0)
+    assert out.splitlines()[2] == "interop fd 1 empty 0 same 1 order 1 0"

@@ -121,3 +121,15 @@ def test_a_second_process_imports_the_meshes_by_file_descriptor(ctx, tmp_path):
         srv.close()
     assert child.returncode == 0
     assert got == want.hexdigest()
+
+
+@pytest.mark.gpu
+def test_device_write_then_read_round_trips(ctx):
+    import ctypes as C
+    L = cb.lib()
+    buf = cb.InteropBuffer(ctx, 4096)
+    data = np.arange(1000, dtype=np.uint32) * np.uint32(2654435761)
+    ctx.check(L.ctc_device_write(ctx.handle, buf.ptr + 64, data.ctypes.data, data.nbytes))
+    assert np.array_equal(buf.read(64, data.nbytes, np.uint32), data)
+    ctx.check(L.ctc_device_write(ctx.handle, buf.ptr, None, 0))           # nothing to copy: just a synchronisation
+    buf.close()

@@ -58,3 +58,16 @@ def test_order_spans_rejects_what_the_mesh_call_rejects(ctx):
     with pytest.raises(AssertionError):
         cb.order_spans(bad, shape, 32, ctx)
     assert cb.order_spans(startup_leaves()[:0], shape, 32, ctx).shape == (0,)
+
+
+@pytest.mark.gpu
+def test_culling_and_surface_first_compose(ctx):
+    shape = cb.Mandelbulb.classic(6, 2.5, fast=True)
+    spans = cb.tile_volume(shape.bounding_box(), 8)[::3]          # 171 spans, many of them empty space
+    ref, tr = cb.generate_for_boxes(spans, shape, 32, ctx)
+    got, tg = cb.generate_for_boxes(spans, shape, 32, ctx, cull=True, surface_first=True)
+    assert tg.vertices == tr.vertices and tg.faces == tr.faces
+    for k in range(len(spans)):
+        a, b = got.mesh(k), ref.mesh(k)
+        assert np.array_equal(a.indices, b.indices), k
+        assert np.array_equal(a.vertices.view(np.uint32), b.vertices.view(np.uint32)), k
